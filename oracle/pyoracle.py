@@ -1,0 +1,216 @@
+"""ctypes wrapper over oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+(coupe_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+W_I32, W_I64, W_F64 = 0, 1, 2
+_NP_OF = {W_I32: np.int32, W_I64: np.int64, W_F64: np.float64}
+
+
+class _Trace(C.Structure):
+    _fields_ = [
+        ("visited", C.c_void_p),
+        ("split_pos", C.c_void_p),
+        ("weight_left", C.c_void_p),
+        ("sum", C.c_void_p),
+        ("n_items", C.c_void_p),
+        ("n_left", C.c_void_p),
+        ("iters", C.c_void_p),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile (g++)."""
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(
+        os.path.join(_HERE, "rcb_oracle.cpp")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "clean", "all"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.oracle_rcb.restype = C.c_int
+        _lib.oracle_rcb.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_size_t, C.c_double, C.c_int, C.POINTER(_Trace),
+                                    C.POINTER(C.c_int)]
+        _lib.oracle_rib.restype = C.c_int
+        _lib.oracle_rib.argtypes = _lib.oracle_rcb.argtypes + [C.c_void_p]
+        _lib.oracle_split_u32.restype = C.c_size_t
+        _lib.oracle_split_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_float,
+                                          C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        _lib.oracle_reorder_split.restype = C.c_size_t
+        _lib.oracle_reorder_split.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
+        _lib.oracle_bbox.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_inertia_matrix.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        _lib.oracle_inertia_vector.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oracle_householder.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oracle_fix_shift.restype = C.c_int
+        _lib.oracle_fix_shift.argtypes = [C.c_size_t, C.c_double]
+        _lib.oracle_imbalance.restype = C.c_double
+        _lib.oracle_imbalance.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_int]
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+@dataclass
+class Trace:
+    visited: np.ndarray
+    split_pos: np.ndarray
+    weight_left: np.ndarray
+    sum: np.ndarray
+    n_items: np.ndarray
+    n_left: np.ndarray
+    iters: np.ndarray
+    shift: int = 0
+
+
+def _wtype_of(weights) -> int:
+    dt = np.asarray(weights).dtype
+    if dt == np.int32:
+        return W_I32
+    if dt == np.int64:
+        return W_I64
+    if dt == np.float64:
+        return W_F64
+    raise TypeError(f"unsupported weight dtype {dt}")
+
+
+def _prep(points, weights):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    assert pts.ndim == 2
+    n, dim = pts.shape
+    w = np.asarray(weights)
+    wtype = _wtype_of(w)
+    is_const = w.ndim == 0
+    w = np.ascontiguousarray(w.reshape(-1))
+    if not is_const and w.shape[0] != n:
+        raise ValueError("length mismatch")  # COUPE_ERR_LEN_MISMATCH at the FFI
+    return pts, n, dim, w, wtype, is_const
+
+
+def _run(fn, points, weights, iter_count, tolerance, mode, want_trace, extra=()):
+    pts, n, dim, w, wtype, is_const = _prep(points, weights)
+    part = np.zeros(n, dtype=np.uint64)
+    shift = C.c_int(0)
+    tr = None
+    trp = None
+    if want_trace:
+        m = max((1 << iter_count) - 1, 1)
+        tr = Trace(np.zeros(m, np.uint8), np.zeros(m, np.float32), np.zeros(m, np.float64),
+                   np.zeros(m, np.float64), np.zeros(m, np.uint64), np.zeros(m, np.uint64),
+                   np.zeros(m, np.uint32))
+        ct = _Trace(*(a.ctypes.data for a in (tr.visited, tr.split_pos, tr.weight_left, tr.sum,
+                                               tr.n_items, tr.n_left, tr.iters)))
+        trp = C.byref(ct)
+    err = fn(part.ctypes.data, dim, n, pts.ctypes.data, wtype, w.ctypes.data, int(is_const),
+             iter_count, float(tolerance), int(mode), trp, C.byref(shift), *extra)
+    if err != 0:
+        raise RuntimeError(f"oracle returned coupe_err {err}")
+    if tr is not None:
+        tr.shift = shift.value
+    return part, tr
+
+
+def rcb(points, weights, iter_count, tolerance=0.05, mode=0, trace=False):
+    """Oracle Rcb.  points (n, D) f64; weights: int32/int64/float64 array of n,
+    or a 0-d array for a constant.  mode 0 native sums, 1 fixed-point f64 sums."""
+    part, tr = _run(lib().oracle_rcb, points, weights, iter_count, tolerance, mode, trace)
+    return (part, tr) if trace else part
+
+
+def rib(points, weights, iter_count, tolerance=0.05, mode=0, trace=False, return_matrix=False):
+    dim = np.asarray(points).shape[1]
+    mat = np.zeros((dim, dim), dtype=np.float64)
+    part, tr = _run(lib().oracle_rib, points, weights, iter_count, tolerance, mode, trace,
+                    extra=(mat.ctypes.data,))
+    out = (part,)
+    if trace:
+        out += (tr,)
+    if return_matrix:
+        out += (mat,)
+    return out if len(out) > 1 else part
+
+
+def split_u32(x, w, tolerance, lo, hi):
+    x = np.ascontiguousarray(x, dtype=np.float32).copy()
+    w = np.ascontiguousarray(w, dtype=np.uint32).copy()
+    wl = C.c_uint32(0)
+    sp = C.c_float(0)
+    nl = lib().oracle_split_u32(x.ctypes.data, w.ctypes.data, x.shape[0], float(tolerance),
+                                float(lo), float(hi), C.byref(wl), C.byref(sp))
+    return x, w, int(nl), int(wl.value), np.float32(sp.value)
+
+
+def reorder_split(x, pivot):
+    x = np.ascontiguousarray(x, dtype=np.float32).copy()
+    l = lib().oracle_reorder_split(x.ctypes.data, x.shape[0], int(pivot))
+    return x, int(l)
+
+
+def bbox(points):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n, dim = pts.shape
+    lo = np.zeros(dim)
+    hi = np.zeros(dim)
+    lib().oracle_bbox(dim, n, pts.ctypes.data, lo.ctypes.data, hi.ctypes.data)
+    return lo, hi
+
+
+def inertia_matrix(points):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n, dim = pts.shape
+    m = np.zeros((dim, dim))
+    lib().oracle_inertia_matrix(dim, n, pts.ctypes.data, m.ctypes.data)
+    return m
+
+
+def inertia_vector(mat):
+    m = np.ascontiguousarray(mat, dtype=np.float64)
+    v = np.zeros(m.shape[0])
+    lib().oracle_inertia_vector(m.shape[0], m.ctypes.data, v.ctypes.data)
+    return v
+
+
+def householder(v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    h = np.zeros((v.shape[0], v.shape[0]))
+    lib().oracle_householder(v.shape[0], v.ctypes.data, h.ctypes.data)
+    return h
+
+
+def fix_shift(n, maxabs):
+    return lib().oracle_fix_shift(int(n), float(maxabs))
+
+
+def imbalance(num_parts, partition, weights):
+    part = np.ascontiguousarray(partition, dtype=np.uint64)
+    w = np.asarray(weights)
+    is_const = w.ndim == 0
+    wtype = _wtype_of(w)
+    w = np.ascontiguousarray(w.reshape(-1))
+    return lib().oracle_imbalance(int(num_parts), part.shape[0], part.ctypes.data, wtype,
+                                  w.ctypes.data, int(is_const))
+
+
+def num_threads():
+    return lib().oracle_num_threads()
