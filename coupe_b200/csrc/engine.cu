@@ -1,0 +1,687 @@
+// engine.cu — host side of the B200 RCB/RIB engine and its device-level C ABI
+// (include/coupe_b200.h).  One context per process and GPU; the level loop
+// below replaces the recursion of coupe/src/algorithms/recursive_bisection.rs
+// (rcb :644-705, rcb_recurse :575-642) with one dense sweep per tree level
+// plus sparse refinement sweeps only while some node's bisection is undecided.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <nccl.h>
+#include <string>
+#include <vector>
+
+#include "../../include/coupe.h"
+#include "../../include/coupe_b200.h"
+#include "rcb_kernels.cuh"
+
+namespace {
+
+using namespace cb;
+
+constexpr int MAX_LEVELS = 20;  // 2^20 parts; node tables are replicated on every GPU
+
+struct CudaFail {
+  cudaError_t err;
+  const char *what;
+};
+#define CU(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) throw CudaFail{e__, #call}; \
+  } while (0)
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  bool load() {
+    if (handle) return true;
+    // Resolve against the NCCL already mapped into the process (torch's) when there is one.
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+struct NcclFail {
+  ncclResult_t err;
+};
+#define NC(call)                                  \
+  do {                                            \
+    ncclResult_t r__ = (call);                    \
+    if (r__ != ncclSuccess) throw NcclFail{r__}; \
+  } while (0)
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CU(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    const size_t want = ((bytes + (1u << 20) - 1) >> 20) << 20;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+};
+
+// --- small dense symmetric eigen / Householder helpers for RIB (host, f64) ----
+// geometry.rs:286-319.  The reference calls nalgebra's symmetric_eigen; a cyclic
+// Jacobi iteration gives the same eigenvector up to rounding (RIB).
+void principal_axis(int D, const double *m, double *v) {
+  double a[3][3] = {{0}}, q[3][3] = {{0}};
+  for (int r = 0; r < D; ++r)
+    for (int s = 0; s < D; ++s) {
+      a[r][s] = 0.5 * (m[r * D + s] + m[s * D + r]);
+      q[r][s] = r == s;
+    }
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0;
+    for (int r = 0; r < D; ++r)
+      for (int s = r + 1; s < D; ++s) off += std::fabs(a[r][s]);
+    if (off == 0.0) break;
+    for (int i = 0; i < D; ++i)
+      for (int j = i + 1; j < D; ++j) {
+        if (a[i][j] == 0.0) continue;
+        const double tau = (a[j][j] - a[i][i]) / (2.0 * a[i][j]);
+        const double t = std::copysign(1.0, tau) / (std::fabs(tau) + std::hypot(1.0, tau));
+        const double c = 1.0 / std::hypot(1.0, t), s = t * c;
+        for (int r = 0; r < D; ++r) {  // A <- A J
+          const double x = a[r][i], y = a[r][j];
+          a[r][i] = c * x - s * y;
+          a[r][j] = s * x + c * y;
+        }
+        for (int r = 0; r < D; ++r) {  // A <- J^T A
+          const double x = a[i][r], y = a[j][r];
+          a[i][r] = c * x - s * y;
+          a[j][r] = s * x + c * y;
+        }
+        for (int r = 0; r < D; ++r) {  // Q <- Q J
+          const double x = q[r][i], y = q[r][j];
+          q[r][i] = c * x - s * y;
+          q[r][j] = s * x + c * y;
+        }
+      }
+  }
+  int best = 0;
+  for (int d = 1; d < D; ++d)
+    if (a[d][d] > a[best][best]) best = d;
+  for (int d = 0; d < D; ++d) v[d] = q[d][best];
+}
+
+bool ulps_close(double a, double b) {  // approx::Ulps::default() on f64: eps, then 4 ulps
+  if (std::fabs(a - b) <= 2.220446049250313e-16) return true;
+  if (std::signbit(a) != std::signbit(b)) return false;
+  int64_t ia, ib;
+  memcpy(&ia, &a, 8);
+  memcpy(&ib, &b, 8);
+  return (ia > ib ? ia - ib : ib - ia) <= 4;
+}
+
+// H = I - 2 w w^T / (w^T w), w = v + sign * |v| e0; identity if v is parallel to e0.
+void reflection(int D, const double *v, double *h) {
+  double norm = 0;
+  for (int d = 0; d < D; ++d) norm += v[d] * v[d];
+  norm = std::sqrt(norm);
+  for (int r = 0; r < D; ++r)
+    for (int s = 0; s < D; ++s) h[r * D + s] = r == s;
+  bool par = true;
+  for (int d = 0; d < D; ++d) par = par && ulps_close(v[d] / norm, d == 0 ? 1.0 : 0.0);
+  if (par) return;
+  const double sign = v[0] > 0.0 ? -1.0 : 1.0;
+  double w[3] = {0, 0, 0}, ww = 0;
+  for (int d = 0; d < D; ++d) w[d] = v[d] + (d == 0 ? sign * norm : 0.0);
+  for (int d = 0; d < D; ++d) ww += w[d] * w[d];
+  for (int r = 0; r < D; ++r)
+    for (int s = 0; s < D; ++s) h[r * D + s] -= 2.0 * w[r] * w[s] / ww;
+}
+
+bool inverse(int D, const double *a, double *o) {  // cofactor inverse (try_inverse, geometry.rs:219)
+  if (D == 2) {
+    const double det = a[0] * a[3] - a[1] * a[2];
+    if (det == 0) return false;
+    o[0] = a[3] / det; o[1] = -a[1] / det; o[2] = -a[2] / det; o[3] = a[0] / det;
+    return true;
+  }
+  const double c00 = a[4] * a[8] - a[7] * a[5], c01 = a[3] * a[8] - a[6] * a[5],
+               c02 = a[3] * a[7] - a[6] * a[4];
+  const double det = a[0] * c00 - a[1] * c01 + a[2] * c02;
+  if (det == 0) return false;
+  o[0] = c00 / det;
+  o[1] = (a[2] * a[7] - a[8] * a[1]) / det;
+  o[2] = (a[1] * a[5] - a[4] * a[2]) / det;
+  o[3] = -c01 / det;
+  o[4] = (a[0] * a[8] - a[6] * a[2]) / det;
+  o[5] = (a[2] * a[3] - a[5] * a[0]) / det;
+  o[6] = c02 / det;
+  o[7] = (a[1] * a[6] - a[7] * a[0]) / det;
+  o[8] = (a[0] * a[4] - a[3] * a[1]) / det;
+  return true;
+}
+
+}  // namespace
+
+struct coupe_b200_ctx {
+  int device = 0;
+  int num_sms = 148;
+  size_t max_smem = 0;
+  std::mutex mu;
+  // scratch
+  Buf xcols, ids, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, rtable, gp,
+      tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
+  uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // options
+  int kmax_a = 8, nb_smem_log2 = 14, kmax_refine = 10, force_global = 0, trace_on = 1;
+  // last call
+  coupe_b200_stats stats{};
+  uint32_t trace_levels = 0;
+  bool funcs_ready = false;
+};
+
+namespace {
+
+size_t sweep_smem_bytes(int level, int k, int copies_log2, bool table_in_smem) {
+  const size_t nb = (size_t)1 << (level + k);
+  size_t b = nb * ((size_t)1 << copies_log2) * 12;
+  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4);
+  return b;
+}
+
+template <int WT>
+void launch_sweep_first(bool smem, int grid, size_t bytes, cudaStream_t st, const SweepArgs &a) {
+  if (smem)
+    sweep_first_kernel<WT, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else
+    sweep_first_kernel<WT, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+}
+
+void prepare_funcs(coupe_b200_ctx *c) {
+  if (c->funcs_ready) return;
+  const int m = (int)c->max_smem;
+#define SETATTR(fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, m))
+  SETATTR((sweep_first_kernel<WT_I32, true>));
+  SETATTR((sweep_first_kernel<WT_I64, true>));
+  SETATTR((sweep_first_kernel<WT_F64, true>));
+  SETATTR((sweep_first_kernel<WT_CONST, true>));
+  SETATTR((sweep_first_kernel<WT_I32, false>));
+  SETATTR((sweep_first_kernel<WT_I64, false>));
+  SETATTR((sweep_first_kernel<WT_F64, false>));
+  SETATTR((sweep_first_kernel<WT_CONST, false>));
+#undef SETATTR
+  c->funcs_ready = true;
+}
+
+struct Run {
+  coupe_b200_ctx *c;
+  cudaStream_t st;
+  coupe_b200_stats &s;
+  void launched(int n = 1) { s.kernel_launches += n; }
+  void allreduce(void *buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+    if (c->world <= 1) return;
+    NC(g_nccl.AllReduce(buf, buf, count, dt, op, c->comm, st));
+    s.collectives += 1;
+  }
+  void sync() {
+    CU(cudaStreamSynchronize(st));
+    s.host_syncs += 1;
+  }
+};
+
+int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, uintptr_t dim,
+             uintptr_t n, const double *pts, int wtype, const void *w_dev, const void *wconst_host,
+             uintptr_t iter_count, double tolerance) {
+  if (dim != 2 && dim != 3) return COUPE_ERR_BAD_DIMENSION;
+  if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
+  if (!w_dev && !wconst_host) return COUPE_ERR_CRASH;
+  if (iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_CRASH;
+  if (n >= ((uintptr_t)1 << 32) * 4) return COUPE_ERR_CRASH;
+  CU(cudaSetDevice(c->device));
+  prepare_funcs(c);
+  const int D = (int)dim, L = (int)iter_count;
+  c->stats = coupe_b200_stats{};
+  coupe_b200_stats &S = c->stats;
+  S.n_local = n;
+  S.levels = (uint32_t)L;
+  Run R{c, st, S};
+
+  // ---- scratch -------------------------------------------------------------
+  const size_t npad = ((n + 3) / 4) * 4 + 4;
+  c->xcols.ensure(npad * sizeof(float) * 3);
+  c->ids.ensure(npad * sizeof(uint32_t));
+  const size_t nb_smem = (size_t)1 << c->nb_smem_log2;
+  c->part_w.ensure((size_t)c->num_sms * nb_smem * 8);
+  c->part_min.ensure((size_t)c->num_sms * nb_smem * 4);
+  size_t hist_entries = std::max<size_t>(nb_smem, (size_t)1 << 17);
+  if (L > 0) hist_entries = std::max<size_t>(hist_entries, (size_t)2 << (L - 1));
+  c->hist_w.ensure(hist_entries * 8);
+  c->hist_min.ensure(hist_entries * 4);
+  const size_t max_nodes = (size_t)1 << (L > 0 ? L - 1 : 0);
+  c->nodes_a.ensure(max_nodes * sizeof(NodeState));
+  c->nodes_b.ensure(max_nodes * sizeof(NodeState));
+  c->table_a.ensure(max_nodes * sizeof(float4));
+  c->table_b.ensure(max_nodes * sizeof(float4));
+  c->rtable.ensure(max_nodes * sizeof(float4));
+  c->gp.ensure(sizeof(GlobalParams));
+  c->mom_partial.ensure((size_t)c->num_sms * 8 * 16 * sizeof(double));
+  const size_t tr_n = L > 0 ? ((size_t)1 << L) - 1 : 1;
+  Trace tr{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (c->trace_on) {
+    c->tr_visited.ensure(tr_n);
+    c->tr_split.ensure(tr_n * 4);
+    c->tr_wl.ensure(tr_n * 8);
+    c->tr_sum.ensure(tr_n * 8);
+    c->tr_iters.ensure(tr_n * 4);
+    CU(cudaMemsetAsync(c->tr_visited.p, 0, tr_n, st));
+    tr = Trace{c->tr_visited.as<uint8_t>(), c->tr_split.as<float>(), c->tr_wl.as<double>(),
+               c->tr_sum.as<double>(), c->tr_iters.as<uint32_t>()};
+    c->trace_levels = (uint32_t)L;
+  }
+  GlobalParams *gp = c->gp.as<GlobalParams>();
+  float *x[3] = {c->xcols.as<float>(), c->xcols.as<float>() + npad, c->xcols.as<float>() + 2 * npad};
+  uint32_t *ids = c->ids.as<uint32_t>();
+
+  // ---- global point count ---------------------------------------------------
+  unsigned long long n_global = n;
+  if (c->world > 1) {
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(c->hist_w.p);
+    CU(cudaMemcpyAsync(d, &n_global, 8, cudaMemcpyHostToDevice, st));
+    R.allreduce(d, 1, ncclUint64, ncclSum);
+    CU(cudaMemcpyAsync(c->h_pinned, d, 8, cudaMemcpyDeviceToHost, st));
+    R.sync();
+    memcpy(&n_global, c->h_pinned, 8);
+  }
+  S.n_global = n_global;
+  if (n_global == 0) return COUPE_ERR_OK;  // BoundingBox::from_points -> None (:685-688)
+  if (L == 0) {                            // iter_count == 0: every id is 0
+    if (n) CU(cudaMemsetAsync(part_dev, 0, n * sizeof(uint64_t), st));
+    R.sync();
+    return COUPE_ERR_OK;
+  }
+
+  // ---- RIB: principal axis, obb_to_aabb matrix ------------------------------
+  Mat3 rot{};
+  if (rib) {
+    const int mgrid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 8, (n + 255) / 256));
+    double *partial = c->mom_partial.as<double>();
+    double *dsums = reinterpret_cast<double *>(c->hist_w.p);
+    double hs[16];
+    auto reduce_to_host = [&](int nv) {
+      moments_final_kernel<<<1, 32, 0, st>>>(partial, mgrid, nv, dsums);
+      R.launched();
+      R.allreduce(dsums, nv, ncclFloat64, ncclSum);
+      CU(cudaMemcpyAsync(c->h_pinned, dsums, nv * 8, cudaMemcpyDeviceToHost, st));
+      R.sync();
+      memcpy(hs, c->h_pinned, nv * 8);
+    };
+    if (D == 2) moments_partial_kernel<2, false><<<mgrid, 256, 0, st>>>(pts, n, partial, 0, 0, 0);
+    else moments_partial_kernel<3, false><<<mgrid, 256, 0, st>>>(pts, n, partial, 0, 0, 0);
+    R.launched();
+    reduce_to_host(D);
+    double cen[3] = {0, 0, 0};
+    for (int d = 0; d < D; ++d) cen[d] = hs[d] / (double)n_global;  // geometry.rs:274-275
+    if (D == 2)
+      moments_partial_kernel<2, true><<<mgrid, 256, 0, st>>>(pts, n, partial, cen[0], cen[1], 0);
+    else
+      moments_partial_kernel<3, true><<<mgrid, 256, 0, st>>>(pts, n, partial, cen[0], cen[1], cen[2]);
+    R.launched();
+    reduce_to_host(D * D);
+    double v[3], h[9], inv[9];
+    principal_axis(D, hs, v);
+    reflection(D, v, h);
+    if (!inverse(D, h, inv)) return COUPE_ERR_CRASH;  // `.unwrap()` on try_inverse
+    for (int k = 0; k < D * D; ++k) rot.m[k] = S.matrix[k] = inv[k];
+  }
+
+  // ---- prologue: narrow, bbox, max |w| --------------------------------------
+  {
+    GlobalParams init{};
+    for (int k = 0; k < 8; ++k) init.bbox_keys[k] = KEY_EMPTY;
+    init.leaf_min = 0xFFFFFFFFu;
+    static_assert(sizeof(GlobalParams) % 4 == 0, "");
+    CU(cudaMemcpyAsync(gp, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const size_t ngroups = (n + 3) / 4;
+    const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 8, (ngroups + 255) / 256));
+    const double *wf = (wtype == WT_F64 && w_dev) ? static_cast<const double *>(w_dev) : nullptr;
+    const int pa = ((uintptr_t)pts % 16) == 0, wa = ((uintptr_t)w_dev % 16) == 0;
+    if (D == 2) {
+      if (rib) narrow_kernel<2, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
+      else narrow_kernel<2, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
+    } else {
+      if (rib) narrow_kernel<3, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
+      else narrow_kernel<3, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
+    }
+    R.launched();
+    if (c->world > 1) {
+      R.allreduce(gp->bbox_keys, 8, ncclUint32, ncclMin);
+      // max |w|: bit patterns of non-negative doubles order like unsigned integers
+      R.allreduce(&gp->maxabs_bits, 1, ncclUint64, ncclMax);
+    }
+  }
+  long long wconst_i = 1;
+  double wconst_f = 0.0;
+  const int w_is_const = w_dev == nullptr;
+  if (w_is_const) {
+    if (wtype == WT_I32) wconst_i = *static_cast<const int *>(wconst_host);
+    else if (wtype == WT_I64) wconst_i = *static_cast<const long long *>(wconst_host);
+    else wconst_f = *static_cast<const double *>(wconst_host);
+  }
+  NodeState *cur = c->nodes_a.as<NodeState>(), *nxt = c->nodes_b.as<NodeState>();
+  float4 *tab_cur = c->table_a.as<float4>(), *tab_next = c->table_b.as<float4>();
+  float4 *rtable = c->rtable.as<float4>();
+  init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, D, wtype, w_is_const, wconst_i, wconst_f,
+                                    n_global);
+  R.launched();
+
+  const int sweep_wt = w_is_const ? WT_CONST : wtype;
+  const size_t ngroups = (n + 3) / 4;
+  const int sweep_grid =
+      std::max(1, (int)std::min<size_t>((size_t)c->num_sms, (ngroups + SWEEP_THREADS - 1) / SWEEP_THREADS));
+  const int refine_grid =
+      std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
+  unsigned long long *hist_w = c->hist_w.as<unsigned long long>();
+  uint32_t *hist_min = c->hist_min.as<uint32_t>();
+  const int w_vec = ((uintptr_t)w_dev % 16) == 0;
+
+  auto run_walk = [&](int level, int k, int first) {
+    CU(cudaMemsetAsync(&gp->unresolved, 0, 4, st));
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, rtable, tr, tolerance,
+                level, k, D, first, level == L - 1, w_is_const};
+    const size_t bytes = ((size_t)2 << k) * 12;
+    const int nodes = 1 << level;
+    if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    else if (wtype == WT_I64) walk_kernel<WT_I64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    R.launched();
+    CU(cudaMemcpyAsync(c->h_pinned, &gp->unresolved, 4, cudaMemcpyDeviceToHost, st));
+    R.sync();
+    return c->h_pinned[0];
+  };
+
+  for (int level = 0; level < L; ++level) {
+    const int axis = level % D, prev_axis = (level + D - 1) % D;
+    // ---- dense first pass ----------------------------------------------------
+    int k = std::min(c->kmax_a, c->nb_smem_log2 - level);
+    bool smem = !c->force_global && k >= 1;
+    int copies_log2 = 0;
+    bool table_in_smem = true;
+    size_t bytes = 0;
+    if (smem) {
+      copies_log2 = std::min(5, c->nb_smem_log2 - (level + k));
+      bytes = sweep_smem_bytes(level, k, copies_log2, true);
+      if (bytes > c->max_smem) {
+        table_in_smem = false;
+        bytes = sweep_smem_bytes(level, k, copies_log2, false);
+      }
+      if (bytes > c->max_smem) smem = false;
+    }
+    if (!smem) {
+      k = std::max(1, std::min(c->kmax_a, 17 - level));
+      copies_log2 = 0;
+      table_in_smem = ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4) <= 64 * 1024;
+      bytes = table_in_smem ? ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4) : 0;
+    }
+    const uint32_t nb = 1u << (level + k);
+    SweepArgs sa{};
+    sa.n = n;
+    sa.x = x[axis];
+    sa.xp = x[prev_axis];
+    sa.ids = ids;
+    sa.w = w_dev;
+    sa.gp = gp;
+    sa.table = tab_cur;
+    sa.part_w = c->part_w.as<long long>();
+    sa.part_min = c->part_min.as<uint32_t>();
+    sa.hist_w = hist_w;
+    sa.hist_min = hist_min;
+    sa.level = level;
+    sa.k = k;
+    sa.copies_log2 = copies_log2;
+    sa.table_in_smem = table_in_smem;
+    sa.w_vec = w_vec;
+    if (!smem) {
+      fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb);
+      R.launched();
+    }
+    switch (sweep_wt) {
+      case WT_I32: launch_sweep_first<WT_I32>(smem, sweep_grid, bytes, st, sa); break;
+      case WT_I64: launch_sweep_first<WT_I64>(smem, sweep_grid, bytes, st, sa); break;
+      case WT_F64: launch_sweep_first<WT_F64>(smem, sweep_grid, bytes, st, sa); break;
+      default: launch_sweep_first<WT_CONST>(smem, sweep_grid, bytes, st, sa); break;
+    }
+    R.launched();
+    S.dense_sweeps += 1;
+    if (smem) {
+      reduce_partials_kernel<<<(nb + 255) / 256, 256, 0, st>>>(sa.part_w, sa.part_min, sweep_grid, nb,
+                                                               hist_w, hist_min);
+      R.launched();
+    }
+    R.allreduce(hist_w, nb, ncclUint64, ncclSum);
+    R.allreduce(hist_min, nb, ncclUint32, ncclMin);
+    uint32_t unresolved = run_walk(level, k, 1);
+
+    // ---- sparse refinement passes while some bisection is undecided ----------
+    int guard = 0;
+    while (unresolved > 0) {
+      if (++guard > 400) return COUPE_ERR_CRASH;  // cannot happen: f32 brackets shrink
+      const int kr = std::max(1, std::min(c->kmax_refine, 17 - level));
+      const uint32_t nbr = 1u << (level + kr);
+      fill_hist_kernel<<<(nbr + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nbr);
+      R.launched();
+      RefineArgs ra{n, x[axis], ids, w_dev, gp, rtable, hist_w, hist_min, level, kr};
+      switch (sweep_wt) {
+        case WT_I32: sweep_refine_kernel<WT_I32><<<refine_grid, 512, 0, st>>>(ra); break;
+        case WT_I64: sweep_refine_kernel<WT_I64><<<refine_grid, 512, 0, st>>>(ra); break;
+        case WT_F64: sweep_refine_kernel<WT_F64><<<refine_grid, 512, 0, st>>>(ra); break;
+        default: sweep_refine_kernel<WT_CONST><<<refine_grid, 512, 0, st>>>(ra); break;
+      }
+      R.launched();
+      S.refine_sweeps += 1;
+      R.allreduce(hist_w, nbr, ncclUint64, ncclSum);
+      R.allreduce(hist_min, nbr, ncclUint32, ncclMin);
+      unresolved = run_walk(level, kr, 0);
+    }
+    std::swap(cur, nxt);
+    std::swap(tab_cur, tab_next);
+  }
+
+  // ---- final ids -------------------------------------------------------------
+  {
+    const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
+    emit_kernel<<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, L, gp,
+                                      reinterpret_cast<unsigned long long *>(part_dev),
+                                      ((uintptr_t)part_dev % 16) == 0);
+    R.launched();
+  }
+  CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
+  R.sync();
+  memcpy(&S.weight_shift, c->h_pinned, 4);
+  CU(cudaGetLastError());
+  return COUPE_ERR_OK;
+}
+
+int guarded(coupe_b200_ctx *c, bool rib, void *stream, uint64_t *part_dev, uintptr_t dim, uintptr_t n,
+            const double *pts, int wtype, const void *w_dev, const void *wconst_host,
+            uintptr_t iter_count, double tolerance) {
+  if (!c) return COUPE_ERR_CRASH;
+  std::lock_guard<std::mutex> lock(c->mu);
+  try {
+    return run_impl(c, rib, static_cast<cudaStream_t>(stream), part_dev, dim, n, pts, wtype, w_dev,
+                    wconst_host, iter_count, tolerance);
+  } catch (const CudaFail &f) {
+    fprintf(stderr, "coupe_b200: CUDA error %s at %s\n", cudaGetErrorString(f.err), f.what);
+    cudaGetLastError();
+    return f.err == cudaErrorMemoryAllocation ? COUPE_ERR_ALLOC : COUPE_ERR_CRASH;
+  } catch (const NcclFail &f) {
+    fprintf(stderr, "coupe_b200: NCCL error %d\n", (int)f.err);
+    return COUPE_ERR_CRASH;
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int coupe_b200_ctx_create(coupe_b200_ctx **out, int device) {
+  if (!out) return COUPE_ERR_CRASH;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return COUPE_ERR_CRASH;  // no CPU fallback
+  }
+  coupe_b200_ctx *c = new (std::nothrow) coupe_b200_ctx();
+  if (!c) return COUPE_ERR_ALLOC;
+  try {
+    c->device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem = prop.sharedMemPerBlockOptin;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pinned), 64 * sizeof(uint32_t) * 4,
+                     cudaHostAllocDefault));
+  } catch (const CudaFail &f) {
+    fprintf(stderr, "coupe_b200: CUDA error %s at %s\n", cudaGetErrorString(f.err), f.what);
+    delete c;
+    return f.err == cudaErrorMemoryAllocation ? COUPE_ERR_ALLOC : COUPE_ERR_CRASH;
+  }
+  *out = c;
+  return COUPE_ERR_OK;
+}
+
+void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (Buf *b : {&c->xcols, &c->ids, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
+                 &c->nodes_b, &c->table_a, &c->table_b, &c->rtable, &c->gp, &c->tr_visited,
+                 &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
+    b->release();
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  delete c;
+}
+
+int coupe_b200_nccl_unique_id(void *out128) {
+  if (!out128 || !g_nccl.load()) return COUPE_ERR_CRASH;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return COUPE_ERR_CRASH;
+  memcpy(out128, &id, 128);
+  return COUPE_ERR_OK;
+}
+
+int coupe_b200_ctx_init_comm(coupe_b200_ctx *c, const void *unique_id128, int rank, int world) {
+  if (!c || !unique_id128 || world < 1 || rank < 0 || rank >= world) return COUPE_ERR_CRASH;
+  if (world == 1) {
+    c->rank = 0;
+    c->world = 1;
+    return COUPE_ERR_OK;
+  }
+  if (!g_nccl.load()) return COUPE_ERR_CRASH;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (cudaSetDevice(c->device) != cudaSuccess) return COUPE_ERR_CRASH;
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  if (g_nccl.CommInitRank(&c->comm, world, id, rank) != ncclSuccess) return COUPE_ERR_CRASH;
+  c->rank = rank;
+  c->world = world;
+  return COUPE_ERR_OK;
+}
+
+int coupe_b200_rcb_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev, uintptr_t dim,
+                          uintptr_t n, const double *points_dev, int wtype, const void *weights_dev,
+                          const void *wconst_host, uintptr_t iter_count, double tolerance) {
+  return guarded(ctx, false, stream, part_dev, dim, n, points_dev, wtype, weights_dev, wconst_host,
+                 iter_count, tolerance);
+}
+
+int coupe_b200_rib_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev, uintptr_t dim,
+                          uintptr_t n, const double *points_dev, int wtype, const void *weights_dev,
+                          const void *wconst_host, uintptr_t iter_count, double tolerance) {
+  return guarded(ctx, true, stream, part_dev, dim, n, points_dev, wtype, weights_dev, wconst_host,
+                 iter_count, tolerance);
+}
+
+int coupe_b200_last_stats(const coupe_b200_ctx *ctx, coupe_b200_stats *out) {
+  if (!ctx || !out) return COUPE_ERR_CRASH;
+  *out = ctx->stats;
+  return COUPE_ERR_OK;
+}
+
+int coupe_b200_last_trace(coupe_b200_ctx *c, uint8_t *visited, float *split_pos, double *weight_left,
+                          double *sum, uint32_t *iters) {
+  if (!c || !c->trace_on) return COUPE_ERR_CRASH;
+  std::lock_guard<std::mutex> lock(c->mu);
+  const size_t m = c->trace_levels > 0 ? ((size_t)1 << c->trace_levels) - 1 : 0;
+  if (m == 0) return COUPE_ERR_OK;
+  if (cudaSetDevice(c->device) != cudaSuccess) return COUPE_ERR_CRASH;
+  bool ok = true;
+  if (visited) ok = ok && cudaMemcpy(visited, c->tr_visited.p, m, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (split_pos) ok = ok && cudaMemcpy(split_pos, c->tr_split.p, m * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (weight_left) ok = ok && cudaMemcpy(weight_left, c->tr_wl.p, m * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (sum) ok = ok && cudaMemcpy(sum, c->tr_sum.p, m * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (iters) ok = ok && cudaMemcpy(iters, c->tr_iters.p, m * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+  return ok ? COUPE_ERR_OK : COUPE_ERR_CRASH;
+}
+
+int coupe_b200_reserve(coupe_b200_ctx *c, uintptr_t n, uintptr_t dim, uintptr_t iter_count) {
+  if (!c || (dim != 2 && dim != 3) || iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_CRASH;
+  std::lock_guard<std::mutex> lock(c->mu);
+  try {
+    CU(cudaSetDevice(c->device));
+    const size_t npad = ((n + 3) / 4) * 4 + 4;
+    c->xcols.ensure(npad * sizeof(float) * 3);
+    c->ids.ensure(npad * sizeof(uint32_t));
+  } catch (const CudaFail &f) {
+    cudaGetLastError();
+    return f.err == cudaErrorMemoryAllocation ? COUPE_ERR_ALLOC : COUPE_ERR_CRASH;
+  }
+  return COUPE_ERR_OK;
+}
+
+int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
+  if (!c || !name) return COUPE_ERR_CRASH;
+  std::lock_guard<std::mutex> lock(c->mu);
+  const std::string s(name);
+  if (s == "kmax_a") c->kmax_a = (int)std::max<int64_t>(1, std::min<int64_t>(10, value));
+  else if (s == "nb_smem_log2") c->nb_smem_log2 = (int)std::max<int64_t>(6, std::min<int64_t>(14, value));
+  else if (s == "kmax_refine") c->kmax_refine = (int)std::max<int64_t>(1, std::min<int64_t>(10, value));
+  else if (s == "force_global") c->force_global = value != 0;
+  else if (s == "trace") c->trace_on = value != 0;
+  else return COUPE_ERR_NOT_FOUND;
+  return COUPE_ERR_OK;
+}
+
+const char *coupe_b200_version(void) { return "coupe_b200 0.1 (sm_100a, CUDA " __DATE__ ")"; }
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// ffi.cu — the reference-compatible C ABI (include/coupe.h) on top of the
+// device engine.  Mirrors coupe-ffi/src/lib.rs:69-157 (strerror, data-set
+// constructors), :255-364 (coupe_rcb / coupe_rib) and coupe-ffi/src/data.rs
+// (Array / Constant / Fn data sets): same names, argument meaning and error
+// codes; the work itself runs on the GPU (no CPU fallback).
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/coupe.h"
+#include "../../include/coupe_b200.h"
+
+struct coupe_data {
+  enum Kind { ARRAY, CONSTANT, FN } kind;
+  uintptr_t len;
+  coupe_type type;
+  const void *ptr;      // array base, constant value, or callback context
+  const void *(*i_th)(const void *, uintptr_t);
+};
+
+namespace {
+
+std::mutex g_mu;
+coupe_b200_ctx *g_ctx = nullptr;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    cap = bytes;
+    return true;
+  }
+};
+DevBuf g_pts, g_w, g_part;
+
+coupe_b200_ctx *default_ctx() {
+  if (g_ctx) return g_ctx;
+  int dev = 0;
+  if (const char *e = getenv("COUPE_B200_DEVICE")) dev = atoi(e);
+  if (coupe_b200_ctx_create(&g_ctx, dev) != COUPE_ERR_OK) g_ctx = nullptr;
+  return g_ctx;
+}
+
+size_t type_size(coupe_type t) { return t == COUPE_INT ? 4 : 8; }
+
+// Materialise a Constant or Fn data set into `out` (elem bytes per element);
+// Fn callbacks are evaluated from several threads, as the reference does with rayon.
+bool materialise(const coupe_data *d, size_t elem, std::vector<unsigned char> &out) {
+  try {
+    out.resize((size_t)d->len * elem);
+  } catch (const std::bad_alloc &) {
+    return false;
+  }
+  unsigned char *o = out.data();
+  const size_t n = d->len;
+  unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+  if (n < 65536) nt = 1;
+  auto work = [&](size_t lo, size_t hi) {
+    if (d->kind == coupe_data::CONSTANT) {
+      for (size_t i = lo; i < hi; ++i) memcpy(o + i * elem, d->ptr, elem);
+    } else {
+      for (size_t i = lo; i < hi; ++i) memcpy(o + i * elem, d->i_th(d->ptr, i), elem);
+    }
+  };
+  if (nt == 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+      const size_t lo = std::min(n, (size_t)t * chunk), hi = std::min(n, lo + chunk);
+      if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto &t : th) t.join();
+  }
+  return true;
+}
+
+coupe_err run(bool rib, uintptr_t *partition, uintptr_t dimension, const coupe_data *points,
+              const coupe_data *weights, uintptr_t iter_count, double tolerance) {
+  if (!points || !weights) return COUPE_ERR_CRASH;
+  const uintptr_t n = points->len;
+  if (n != weights->len) return COUPE_ERR_LEN_MISMATCH;  // lib.rs:285-288
+  if (dimension != 2 && dimension != 3) return COUPE_ERR_BAD_DIMENSION;  // lib.rs:297-301
+  if (weights->type != COUPE_INT && weights->type != COUPE_INT64 && weights->type != COUPE_DOUBLE)
+    return COUPE_ERR_BAD_TYPE;
+  std::lock_guard<std::mutex> lock(g_mu);
+  coupe_b200_ctx *ctx = default_ctx();
+  if (!ctx) return COUPE_ERR_CRASH;
+  if (n == 0) return COUPE_ERR_OK;  // nothing to write (recursive_bisection.rs:685-688)
+
+  // host views of the inputs
+  std::vector<unsigned char> pts_tmp, w_tmp;
+  const size_t pelem = dimension * sizeof(double);
+  const void *pts_host = points->ptr;
+  if (points->kind != coupe_data::ARRAY) {
+    if (!materialise(points, pelem, pts_tmp)) return COUPE_ERR_ALLOC;
+    pts_host = pts_tmp.data();
+  }
+  const size_t welem = type_size(weights->type);
+  const void *w_host = nullptr;      // per-point weights
+  const void *w_const = nullptr;     // or one constant
+  if (weights->kind == coupe_data::ARRAY) w_host = weights->ptr;
+  else if (weights->kind == coupe_data::CONSTANT) w_const = weights->ptr;
+  else {
+    if (!materialise(weights, welem, w_tmp)) return COUPE_ERR_ALLOC;
+    w_host = w_tmp.data();
+  }
+
+  // host -> device, run, device -> host
+  if (!g_pts.ensure(n * pelem) || !g_part.ensure(n * sizeof(uint64_t))) return COUPE_ERR_ALLOC;
+  if (w_host && !g_w.ensure(n * welem)) return COUPE_ERR_ALLOC;
+  if (cudaMemcpy(g_pts.p, pts_host, n * pelem, cudaMemcpyHostToDevice) != cudaSuccess)
+    return COUPE_ERR_CRASH;
+  if (w_host && cudaMemcpy(g_w.p, w_host, n * welem, cudaMemcpyHostToDevice) != cudaSuccess)
+    return COUPE_ERR_CRASH;
+  auto fn = rib ? coupe_b200_rib_device : coupe_b200_rcb_device;
+  const int err = fn(ctx, nullptr, static_cast<uint64_t *>(g_part.p), dimension, n,
+                     static_cast<const double *>(g_pts.p), (int)weights->type,
+                     w_host ? g_w.p : nullptr, w_const, iter_count, tolerance);
+  if (err != COUPE_ERR_OK) return (coupe_err)err;
+  static_assert(sizeof(uintptr_t) == sizeof(uint64_t), "usize is 64 bit");
+  if (cudaMemcpy(partition, g_part.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return COUPE_ERR_CRASH;
+  return COUPE_ERR_OK;
+}
+
+coupe_data *make(coupe_data::Kind kind, uintptr_t len, coupe_type type, const void *ptr,
+                 const void *(*i_th)(const void *, uintptr_t)) {
+  coupe_data *d = new (std::nothrow) coupe_data;
+  if (!d) return nullptr;
+  d->kind = kind;
+  d->len = len;
+  d->type = type;
+  d->ptr = ptr;
+  d->i_th = i_th;
+  return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *coupe_strerror(enum coupe_err err) {  // messages of coupe-ffi/src/lib.rs:69-110
+  switch (err) {
+    case COUPE_ERR_OK: return "success";
+    case COUPE_ERR_ALLOC: return "allocation failed";
+    case COUPE_ERR_CRASH: return "coupe encountered a bug and crashed";
+    case COUPE_ERR_BAD_DIMENSION: return "this algorithm does not support the given mesh dimension";
+    case COUPE_ERR_BAD_TYPE: return "this algorithm does not support the given type";
+    case COUPE_ERR_BIPART_ONLY: return "this algorithm does not support k-way partitioning";
+    case COUPE_ERR_LEN_MISMATCH:
+      return "input iters (e.g. weights and points) don't have the same length";
+    case COUPE_ERR_NOT_FOUND: return "no partition has been found for the given constraints";
+    case COUPE_ERR_NEG_VALUES: return "this algorithm does not support negative values";
+  }
+  return "unknown error";
+}
+
+void coupe_data_free(coupe_data *data) { delete data; }
+
+coupe_data *coupe_data_array(uintptr_t len, enum coupe_type type, const void *data) {
+  return make(coupe_data::ARRAY, len, type, data, nullptr);
+}
+
+coupe_data *coupe_data_constant(uintptr_t len, enum coupe_type type, const void *value) {
+  return make(coupe_data::CONSTANT, len, type, value, nullptr);
+}
+
+coupe_data *coupe_data_fn(const void *context, uintptr_t len, enum coupe_type type,
+                          const void *(*i_th)(const void *, uintptr_t)) {
+  return make(coupe_data::FN, len, type, context, i_th);
+}
+
+enum coupe_err coupe_rcb(uintptr_t *partition, uintptr_t dimension, const coupe_data *points,
+                         const coupe_data *weights, uintptr_t iter_count, double tolerance) {
+  try {
+    return run(false, partition, dimension, points, weights, iter_count, tolerance);
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;  // catch_unwind -> Crash, lib.rs:62-67
+  }
+}
+
+enum coupe_err coupe_rib(uintptr_t *partition, uintptr_t dimension, const coupe_data *points,
+                         const coupe_data *weights, uintptr_t iter_count, double tolerance) {
+  try {
+    return run(true, partition, dimension, points, weights, iter_count, tolerance);
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;
+  }
+}
+
+}  // extern "C"

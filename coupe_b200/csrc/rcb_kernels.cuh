@@ -1,0 +1,852 @@
+// rcb_kernels.cuh — CUDA kernels (sm_100a) of the level-synchronous RCB engine.
+//
+// Replaces, for ALL nodes of one tree level at once, the per-node loop of the
+// reference (coupe/src/algorithms/recursive_bisection.rs):
+//   narrow_kernel       rcb() prologue :674-688  (f64 -> f32 SoA narrowing, root bbox,
+//                       geometry.rs:33-78) and, for RIB, the obb_to_aabb map (:848)
+//   sweep_first_kernel  the fold of par_rcb_split :478-520, for every candidate cut of
+//                       the next k bisection iterations of every node, fused with the
+//                       part-id update that reorder_split :122-181 + rcb_recurse
+//                       :618-641 perform by physically moving the points
+//   sweep_refine_kernel the same fold restricted to the bracket that survived
+//   walk_kernel         the control flow of par_rcb_split :470-573 and the child
+//                       set-up of rcb_recurse :604-616, one thread block per node
+//   emit_kernel         leaf id store :589-602 and id renumbering :698-702
+//   moments kernels     inertia_matrix geometry.rs:273-284 (RIB)
+//
+// All kernels are bound by HBM bandwidth; DESIGN.md gives the bytes per point.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cb {
+
+constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+enum : int { WT_I32 = 0, WT_I64 = 1, WT_F64 = 2, WT_CONST = 3 };
+enum : int { SIDE_NONE = 0, SIDE_MIN = 1, SIDE_MAX = 2 };
+constexpr int SWEEP_THREADS = 1024;
+constexpr int WALK_THREADS = 128;
+
+// Per-node bisection state; one array per level parity.
+struct NodeState {
+  float box_lo[3], box_hi[3];  // inherited bounding box (f32 view of the reference's f64 box)
+  long long sum;               // node weight (W for ints, fixed point for f64)
+  long long w_below;           // weight of points left of the current bracket
+  float lo, hi;                // current bisection bracket (min, max of the reference)
+  uint32_t min_above;          // key of the smallest coordinate >= hi, KEY_EMPTY if none
+  uint32_t iters;              // candidates evaluated so far
+  uint8_t alive;               // node holds at least one point
+  uint8_t done;                // split decided
+  uint8_t prev_side;           // which bracket end the previous candidate became
+  uint8_t hi_incl;             // hi is still the box bound (points == hi belong to the bracket)
+  uint8_t below_nonempty;      // some point lies left of the bracket
+  uint8_t pad[3];
+};
+
+// Device-resident scalars shared by the kernels of one call.
+struct GlobalParams {
+  double q;                        // 2^-shift: value of one fixed-point unit
+  double scale;                    // 2^shift
+  unsigned long long n_global;     // points over all ranks
+  unsigned long long maxabs_bits;  // bit pattern of max |w| (f64 weights)
+  long long wconst;                // constant weight in accumulator units
+  uint32_t bbox_keys[8];           // [0..D) min keys, [4..4+D) inverted max keys
+  uint32_t unresolved;             // nodes whose bisection needs another pass
+  uint32_t leaf_min;               // smallest non-empty leaf path
+  int shift;
+  int pad;
+};
+
+struct Trace {
+  uint8_t *visited;
+  float *split_pos;
+  double *weight_left;
+  double *sum;
+  uint32_t *iters;
+};
+
+// Order-preserving float <-> uint32 keys (smaller float <=> smaller key).
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+// The reference's candidate: `(min + max) / 2.0` in f32 (recursive_bisection.rs:472).
+__device__ __forceinline__ float midpoint_f32(float lo, float hi) {
+  return __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+}
+
+// ---------------------------------------------------------------------------
+// Prologue: AoS f64 -> SoA f32 (round to nearest even), bounding box, max |w|.
+// ---------------------------------------------------------------------------
+struct Mat3 {
+  double m[9];
+};
+
+template <int D, bool ROT>
+__global__ void __launch_bounds__(256)
+narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
+              float *__restrict__ x1, float *__restrict__ x2, Mat3 rot, GlobalParams *gp,
+              const double *__restrict__ wf64, int pts_aligned, int w_aligned) {
+  float mn[D], mx[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    mn[d] = __int_as_float(0x7f800000);
+    mx[d] = __int_as_float(0xff800000);
+  }
+  double wmax = 0.0;
+  const size_t ngroups = (n + 3) / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const size_t i0 = g * 4;
+    double c[4 * D];
+    const bool full = i0 + 4 <= n;
+    if (full && pts_aligned) {
+      const double2 *src = reinterpret_cast<const double2 *>(pts + i0 * D);
+#pragma unroll
+      for (int v = 0; v < 2 * D; ++v) {
+        const double2 t = __ldcs(src + v);
+        c[2 * v] = t.x;
+        c[2 * v + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4 * D; ++v) c[v] = (i0 * D + v < n * D) ? __ldcs(pts + i0 * D + v) : 0.0;
+    }
+    float o[D][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double p[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) p[d] = c[j * D + d];
+      if (ROT) {  // p' = M p, accumulated column by column, no contraction
+        double r[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          double acc = __dmul_rn(rot.m[a * D], p[0]);
+#pragma unroll
+          for (int b = 1; b < D; ++b) acc = __dadd_rn(acc, __dmul_rn(rot.m[a * D + b], p[b]));
+          r[a] = acc;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) p[d] = r[d];
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float f = __double2float_rn(p[d]);
+        o[d][j] = f;
+        if (i0 + j < n) {
+          mn[d] = f < mn[d] ? f : mn[d];
+          mx[d] = mx[d] < f ? f : mx[d];
+        }
+      }
+    }
+    __stcs(reinterpret_cast<float4 *>(x0 + i0), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+    __stcs(reinterpret_cast<float4 *>(x1 + i0), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+    if (D == 3)
+      __stcs(reinterpret_cast<float4 *>(x2 + i0),
+             make_float4(o[D - 1][0], o[D - 1][1], o[D - 1][2], o[D - 1][3]));
+    if (wf64) {
+      if (full && w_aligned) {
+        const double2 a = __ldcs(reinterpret_cast<const double2 *>(wf64 + i0));
+        const double2 b = __ldcs(reinterpret_cast<const double2 *>(wf64 + i0) + 1);
+        wmax = fmax(wmax, fmax(fmax(fabs(a.x), fabs(a.y)), fmax(fabs(b.x), fabs(b.y))));
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i0 + j < n) wmax = fmax(wmax, fabs(wf64[i0 + j]));
+      }
+    }
+  }
+  // block reduction: warp shuffles, then one atomic per warp
+  uint32_t kmin[D], kmax[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    kmin[d] = f2key(mn[d]);
+    kmax[d] = ~f2key(mx[d]);
+  }
+  unsigned long long wb = (unsigned long long)__double_as_longlong(wmax);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      kmin[d] = min(kmin[d], __shfl_xor_sync(0xffffffffu, kmin[d], s));
+      kmax[d] = min(kmax[d], __shfl_xor_sync(0xffffffffu, kmax[d], s));
+    }
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, wb, s);
+    wb = o > wb ? o : wb;
+  }
+  __shared__ uint32_t s_k[8][8];
+  __shared__ unsigned long long s_w[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      s_k[warp][d] = kmin[d];
+      s_k[warp][4 + d] = kmax[d];
+    }
+    s_w[warp] = wb;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int slot = threadIdx.x;
+    if ((slot & 3) < D) {
+      uint32_t v = KEY_EMPTY;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = min(v, s_k[wv][slot]);
+      atomicMin(&gp->bbox_keys[slot], v);
+    }
+  }
+  if (threadIdx.x == 32 && wf64) {
+    unsigned long long v = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = s_w[wv] > v ? s_w[wv] : v;
+    atomicMax(&gp->maxabs_bits, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Root set-up once the (all-reduced) bounding box and max |w| are known.
+// ---------------------------------------------------------------------------
+__global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *table0, int D,
+                                 int wtype, int w_is_const, long long wconst_i, double wconst_f,
+                                 unsigned long long n_global) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gp->n_global = n_global;
+  // fixed-point shift for f64 weights: min(31 - e, 62 - e - nbits), max|w| < 2^e, n <= 2^nbits
+  int shift = 0;
+  double maxabs = 0.0;
+  if (wtype == WT_F64) {
+    maxabs = w_is_const ? fabs(wconst_f) : __longlong_as_double((long long)gp->maxabs_bits);
+    if (maxabs > 0.0 && maxabs <= 1.7976931348623157e308) {
+      int e;
+      frexp(maxabs, &e);
+      int nbits = 0;
+      while (nbits < 63 && (1ull << nbits) < n_global) ++nbits;
+      shift = min(31 - e, 62 - e - nbits);
+      shift = max(-1000, min(1000, shift));
+    }
+  }
+  gp->shift = shift;
+  gp->scale = ldexp(1.0, shift);
+  gp->q = ldexp(1.0, -shift);
+  long long wc = 1;
+  if (w_is_const) wc = wtype == WT_F64 ? __double2ll_rn(wconst_f * gp->scale) : wconst_i;
+  gp->wconst = wc;
+  gp->unresolved = 0;
+  gp->leaf_min = 0xFFFFFFFFu;
+  NodeState ns;
+  for (int d = 0; d < 3; ++d) {
+    ns.box_lo[d] = d < D ? key2f(gp->bbox_keys[d]) : 0.f;
+    ns.box_hi[d] = d < D ? key2f(~gp->bbox_keys[4 + d]) : 0.f;
+  }
+  ns.sum = 0;
+  ns.w_below = 0;
+  ns.lo = ns.box_lo[0];
+  ns.hi = ns.box_hi[0];
+  ns.min_above = KEY_EMPTY;
+  ns.iters = 0;
+  ns.alive = n_global > 0;
+  ns.done = 0;
+  ns.prev_side = SIDE_NONE;
+  ns.hi_incl = 1;
+  ns.below_nonempty = 0;
+  ns.pad[0] = ns.pad[1] = ns.pad[2] = 0;
+  *root = ns;
+  table0[0] = make_float4(0.f, ns.box_lo[0], ns.box_hi[0], 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// Weight loads: four consecutive weights in accumulator units.
+// ---------------------------------------------------------------------------
+template <int WT>
+__device__ __forceinline__ void load_w4(const void *__restrict__ w, size_t i0, size_t n, bool vec,
+                                        double scale, long long (&out)[4]) {
+  if (WT == WT_CONST) {
+    out[0] = out[1] = out[2] = out[3] = 1;
+  } else if (WT == WT_I32) {
+    const int *p = static_cast<const int *>(w);
+    if (vec) {
+      const int4 v = __ldcs(reinterpret_cast<const int4 *>(p + i0));
+      out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = (i0 + j < n) ? (long long)__ldcs(p + i0 + j) : 0;
+    }
+  } else if (WT == WT_I64) {
+    const long long *p = static_cast<const long long *>(w);
+    if (vec) {
+      const longlong2 a = __ldcs(reinterpret_cast<const longlong2 *>(p + i0));
+      const longlong2 b = __ldcs(reinterpret_cast<const longlong2 *>(p + i0) + 1);
+      out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = (i0 + j < n) ? __ldcs(p + i0 + j) : 0;
+    }
+  } else {
+    const double *p = static_cast<const double *>(w);
+    double t[4];
+    if (vec) {
+      const double2 a = __ldcs(reinterpret_cast<const double2 *>(p + i0));
+      const double2 b = __ldcs(reinterpret_cast<const double2 *>(p + i0) + 1);
+      t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (i0 + j < n) ? __ldcs(p + i0 + j) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = __double2ll_rn(__dmul_rn(t[j], scale));
+  }
+}
+
+template <int WT>
+__device__ __forceinline__ long long load_w1(const void *__restrict__ w, size_t i, double scale) {
+  if (WT == WT_CONST) return 1;
+  if (WT == WT_I32) return (long long)__ldcs(static_cast<const int *>(w) + i);
+  if (WT == WT_I64) return __ldcs(static_cast<const long long *>(w) + i);
+  return __double2ll_rn(__dmul_rn(__ldcs(static_cast<const double *>(w) + i), scale));
+}
+
+// ---------------------------------------------------------------------------
+// Dense sweep: first pass of a level.
+// ---------------------------------------------------------------------------
+struct SweepArgs {
+  size_t n;
+  const float *x;           // coordinate on this level's axis
+  const float *xp;          // coordinate on the previous level's axis (level >= 1)
+  uint32_t *ids;            // in: parent path (level >= 2); out: path at this level (level >= 1)
+  const void *w;            // weights (null for WT_CONST)
+  const GlobalParams *gp;
+  const float4 *table;      // per parent: {parent split, bracket lo, bracket hi, -}
+  long long *part_w;        // SMEM mode: per-block partial histograms [grid][nb]
+  uint32_t *part_min;
+  unsigned long long *hist_w;  // GLOBAL mode: histogram accumulated with L2 atomics
+  uint32_t *hist_min;
+  int level, k;
+  int copies_log2;          // SMEM mode: 2^copies_log2 privatised copies per block
+  int table_in_smem;
+  int w_vec;                // weights are 16-byte aligned
+};
+
+// k dyadic bisection steps for four points at once: returns, per point, the
+// index of the leaf bracket the coordinate falls in (bit j of the path = went
+// right at depth j).  Identical arithmetic to the walk (midpoint_f32).
+__device__ __forceinline__ void descend4(const float (&x)[4], float (&lo)[4], float (&hi)[4],
+                                         int k, uint32_t (&bin)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bin[j] = 0;
+#pragma unroll 1
+  for (int s = 0; s < k; ++s) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mid = midpoint_f32(lo[j], hi[j]);
+      const bool right = !(x[j] < mid);
+      bin[j] = (bin[j] << 1) | (right ? 1u : 0u);
+      lo[j] = right ? mid : lo[j];
+      hi[j] = right ? hi[j] : mid;
+    }
+  }
+}
+
+template <int WT, bool SMEM>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = a.k, level = a.level;
+  const uint32_t nb = 1u << (level + k);  // bins of this level
+  const int ncopy = 1 << a.copies_log2;
+  uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
+  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + (SMEM ? (size_t)nb * ncopy : 0));
+  uint32_t *s_min = reinterpret_cast<uint32_t *>(s_hi + (SMEM ? (size_t)nb * ncopy : 0));
+  float4 *s_table = reinterpret_cast<float4 *>(s_min + (SMEM ? (size_t)nb * ncopy : 0));
+  const int nparents = 1 << (level > 0 ? level - 1 : 0);
+  if (SMEM) {
+    for (uint32_t i = threadIdx.x; i < nb * ncopy; i += blockDim.x) {
+      s_lo[i] = 0;
+      s_hi[i] = 0;
+      s_min[i] = KEY_EMPTY;
+    }
+  }
+  if (a.table_in_smem)
+    for (int i = threadIdx.x; i < nparents; i += blockDim.x) s_table[i] = a.table[i];
+  __syncthreads();
+  const float4 *table = a.table_in_smem ? s_table : a.table;
+  const double scale = (WT == WT_F64) ? a.gp->scale : 1.0;
+  const uint32_t copy_off = SMEM ? ((threadIdx.x >> 5) & (ncopy - 1)) * nb : 0;
+
+  const size_t n = a.n;
+  const size_t ngroups = (n + 3) / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const size_t i0 = g * 4;
+    uint32_t pp[4] = {0, 0, 0, 0};
+    if (level >= 2) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(a.ids + i0));
+      pp[0] = v.x; pp[1] = v.y; pp[2] = v.z; pp[3] = v.w;
+    }
+    float xp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (level >= 1) {
+      const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.xp + i0));
+      xp[0] = v.x; xp[1] = v.y; xp[2] = v.z; xp[3] = v.w;
+    }
+    float x[4];
+    {
+      const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.x + i0));
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+    long long w[4];
+    load_w4<WT>(a.w, i0, n, a.w_vec && (i0 + 4 <= n), scale, w);
+
+    uint32_t path[4];
+    float lo[4], hi[4];
+    const uint32_t pmask = (uint32_t)nparents - 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 e = table[pp[j] & pmask];  // mask keeps padded lanes in range
+      path[j] = level >= 1 ? 2 * pp[j] + (!(xp[j] < e.x) ? 1u : 0u) : 0u;
+      lo[j] = e.y;
+      hi[j] = e.z;
+    }
+    if (level >= 1)
+      __stcs(reinterpret_cast<uint4 *>(a.ids + i0), make_uint4(path[0], path[1], path[2], path[3]));
+    uint32_t bin[4];
+    descend4(x, lo, hi, k, bin);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j >= n) continue;
+      const uint32_t idx = (path[j] << k) + bin[j];
+      const uint32_t key = f2key(x[j]);
+      if (SMEM) {
+        const uint32_t wlo = (uint32_t)w[j];
+        const uint32_t old = atomicAdd(&s_lo[copy_off + idx], wlo);
+        const int hinc = (int)(w[j] >> 32) + ((uint32_t)(old + wlo) < old ? 1 : 0);
+        if (hinc != 0) atomicAdd(&s_hi[copy_off + idx], hinc);
+        if (key < s_min[copy_off + idx]) atomicMin(&s_min[copy_off + idx], key);
+      } else {
+        atomicAdd(&a.hist_w[idx], (unsigned long long)w[j]);
+        if (key < __ldcg(&a.hist_min[idx])) atomicMin(&a.hist_min[idx], key);
+      }
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    long long *pw = a.part_w + (size_t)blockIdx.x * nb;
+    uint32_t *pm = a.part_min + (size_t)blockIdx.x * nb;
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+      unsigned long long acc = 0;
+      uint32_t m = KEY_EMPTY;
+      for (int c = 0; c < ncopy; ++c) {
+        acc += ((unsigned long long)(uint32_t)s_hi[c * nb + i] << 32) + s_lo[c * nb + i];
+        m = min(m, s_min[c * nb + i]);
+      }
+      pw[i] = (long long)acc;
+      pm[i] = m;
+    }
+  }
+}
+
+// Sum / min of the per-block partial histograms.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__restrict__ part_min,
+                       int nblocks, uint32_t nb, unsigned long long *__restrict__ hist_w,
+                       uint32_t *__restrict__ hist_min) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  unsigned long long acc = 0;
+  uint32_t m = KEY_EMPTY;
+  for (int b = 0; b < nblocks; ++b) {
+    acc += (unsigned long long)part_w[(size_t)b * nb + i];
+    m = min(m, part_min[(size_t)b * nb + i]);
+  }
+  hist_w[i] = acc;
+  hist_min[i] = m;
+}
+
+__global__ void __launch_bounds__(256)
+fill_hist_kernel(unsigned long long *hist_w, uint32_t *hist_min, uint32_t nb) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) {
+    hist_w[i] = 0;
+    hist_min[i] = KEY_EMPTY;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sparse sweep: only points inside the surviving bracket of an unresolved node
+// contribute (and only their weights are read).
+// ---------------------------------------------------------------------------
+struct RefineArgs {
+  size_t n;
+  const float *x;
+  const uint32_t *ids;     // path at this level (level >= 1)
+  const void *w;
+  const GlobalParams *gp;
+  const float4 *rtable;    // per node: {lo, hi, hi inclusive, -}; lo > hi when resolved
+  unsigned long long *hist_w;
+  uint32_t *hist_min;
+  int level, k;
+};
+
+template <int WT>
+__global__ void __launch_bounds__(512) sweep_refine_kernel(const RefineArgs a) {
+  const int k = a.k, level = a.level;
+  const double scale = (WT == WT_F64) ? a.gp->scale : 1.0;
+  const size_t n = a.n;
+  const size_t ngroups = (n + 3) / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint32_t nmask = (1u << level) - 1;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const size_t i0 = g * 4;
+    uint32_t path[4] = {0, 0, 0, 0};
+    if (level >= 1) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(a.ids + i0));
+      path[0] = v.x; path[1] = v.y; path[2] = v.z; path[3] = v.w;
+    }
+    float x[4];
+    {
+      const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.x + i0));
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j >= n) continue;
+      const uint32_t p = path[j] & nmask;
+      const float4 e = __ldg(&a.rtable[p]);
+      const bool in = !(x[j] < e.x) && (x[j] < e.y || (e.z != 0.f && x[j] <= e.y));
+      if (!in) continue;
+      float lo = e.x, hi = e.y;
+      uint32_t bin = 0;
+      for (int s = 0; s < k; ++s) {
+        const float mid = midpoint_f32(lo, hi);
+        const bool right = !(x[j] < mid);
+        bin = (bin << 1) | (right ? 1u : 0u);
+        lo = right ? mid : lo;
+        hi = right ? hi : mid;
+      }
+      const long long w = load_w1<WT>(a.w, i0 + j, scale);
+      const uint32_t idx = (p << k) + bin;
+      atomicAdd(&a.hist_w[idx], (unsigned long long)w);
+      const uint32_t key = f2key(x[j]);
+      if (key < __ldcg(&a.hist_min[idx])) atomicMin(&a.hist_min[idx], key);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The bisection walk: one block per node, thread 0 replays the reference's
+// control flow over a dyadic tree built from the node's histogram.
+// ---------------------------------------------------------------------------
+template <int WT>
+struct WOps;
+template <>
+struct WOps<WT_I32> {  // i32 weights wrap in the reference's release build
+  __device__ static long long canon(long long v) { return (long long)(int)v; }
+  __device__ static double f64(long long v, double) { return (double)(int)v; }
+  __device__ static long long sub(long long a, long long b) {
+    return (long long)(int)((unsigned)a - (unsigned)b);
+  }
+  __device__ static bool lt(long long a, long long b, double) { return (int)a < (int)b; }
+};
+template <>
+struct WOps<WT_I64> {
+  __device__ static long long canon(long long v) { return v; }
+  __device__ static double f64(long long v, double) { return (double)v; }
+  __device__ static long long sub(long long a, long long b) {
+    return (long long)((unsigned long long)a - (unsigned long long)b);
+  }
+  __device__ static bool lt(long long a, long long b, double) { return a < b; }
+};
+template <>
+struct WOps<WT_F64> {  // fixed point: value = v * q
+  __device__ static long long canon(long long v) { return v; }
+  __device__ static double f64(long long v, double q) { return __dmul_rn((double)v, q); }
+  __device__ static long long sub(long long a, long long b) {
+    return (long long)((unsigned long long)a - (unsigned long long)b);
+  }
+  __device__ static bool lt(long long a, long long b, double q) { return f64(a, q) < f64(b, q); }
+};
+
+struct WalkArgs {
+  NodeState *cur;            // nodes of this level
+  NodeState *next;           // nodes of the next level (children)
+  const unsigned long long *hist_w;
+  const uint32_t *hist_min;
+  GlobalParams *gp;
+  float4 *table_next;        // per node: {split, lo, hi on the next axis, -}
+  float4 *rtable;            // per node: refinement bracket
+  Trace trace;
+  double tolerance;
+  int level, k, D, first, last_level, w_is_const;
+};
+
+template <int WT>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = a.k;
+  const uint32_t nb = 1u << k;
+  unsigned long long *wtree = reinterpret_cast<unsigned long long *>(smem_raw);  // heap, 2nb
+  uint32_t *mtree = reinterpret_cast<uint32_t *>(wtree + 2 * nb);                 // heap, 2nb
+  const uint32_t p = blockIdx.x;
+  NodeState &ns = a.cur[p];
+  const int axis = a.level % a.D, next_axis = (a.level + 1) % a.D;
+  const uint32_t heap = ((1u << a.level) - 1) + p;
+
+  if (a.first ? !ns.alive : ns.done) {
+    if (a.first && threadIdx.x == 0) {  // empty node: rcb_recurse returns at once (:586-588)
+      ns.done = 1;
+      a.rtable[p] = make_float4(1.f, 0.f, 0.f, 0.f);
+      a.table_next[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!a.last_level) {
+        a.next[2 * p].alive = 0;
+        a.next[2 * p + 1].alive = 0;
+      }
+    }
+    return;
+  }
+  const unsigned long long wscale = a.w_is_const ? (unsigned long long)a.gp->wconst : 1ull;
+  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+    wtree[nb + i] = a.hist_w[(size_t)p * nb + i] * wscale;
+    mtree[nb + i] = a.hist_min[(size_t)p * nb + i];
+  }
+  __syncthreads();
+  for (int d = k - 1; d >= 0; --d) {
+    const uint32_t base = 1u << d;
+    for (uint32_t i = threadIdx.x; i < base; i += blockDim.x) {
+      const uint32_t t = base + i;
+      wtree[t] = wtree[2 * t] + wtree[2 * t + 1];
+      mtree[t] = min(mtree[2 * t], mtree[2 * t + 1]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+
+  using O = WOps<WT>;
+  const double q = a.gp->q;
+  float lo, hi;
+  long long w_below;
+  uint32_t min_above, iters;
+  int prev_side, hi_incl, below_nonempty;
+  if (a.first) {
+    lo = ns.box_lo[axis];  // :604-605
+    hi = ns.box_hi[axis];
+    w_below = 0;
+    min_above = KEY_EMPTY;
+    iters = 0;
+    prev_side = SIDE_NONE;
+    hi_incl = 1;
+    below_nonempty = 0;
+    if (a.level == 0) ns.sum = O::canon((long long)wtree[1]);  // :684, total weight
+  } else {
+    lo = ns.lo; hi = ns.hi;
+    w_below = ns.w_below;
+    min_above = ns.min_above;
+    iters = ns.iters;
+    prev_side = ns.prev_side;
+    hi_incl = ns.hi_incl;
+    below_nonempty = ns.below_nonempty;
+  }
+  const long long sum = ns.sum;
+  const double ideal = O::f64(sum, q) / 2.0;  // :548
+
+  bool finished = false;
+  float split_pos = 0.f;
+  long long weight_left = 0;
+  bool left_alive = false, right_alive = false;
+  uint32_t t = 1;
+  for (int depth = 0; depth < k; ++depth) {
+    const float st = midpoint_f32(lo, hi);  // :472
+    ++iters;
+    const uint32_t L = 2 * t, R = 2 * t + 1;
+    const long long wl = O::canon((long long)((unsigned long long)w_below + wtree[L]));
+    const bool left_empty = mtree[L] == KEY_EMPTY;    // no point in [lo, st)
+    const bool right_empty = mtree[R] == KEY_EMPTY;   // no point in [st, hi)
+    const uint32_t right_min = min(mtree[R], min_above);
+    // `count_left == prev_count_left`: no point between this candidate and the previous one
+    const bool same_count = (prev_side == SIDE_MIN && left_empty) ||
+                            (prev_side == SIDE_MAX && right_empty);
+    if (right_min == KEY_EMPTY) {  // no point on the right of the candidate, :522-545
+      if (same_count) {
+        finished = true;
+        split_pos = hi;
+        weight_left = sum;
+        left_alive = true;
+        right_alive = false;
+        break;
+      }
+      hi = st;
+      hi_incl = 0;
+      prev_side = SIDE_MAX;
+      t = L;
+      continue;
+    }
+    const float pn = key2f(right_min);
+    const float nd = __fsub_rn(pn, st);                       // nearest_distance
+    const double imb = fabs((O::f64(wl, q) - ideal) / ideal);  // :547-551
+    if (same_count || hi <= __fadd_rn(st, nd) || imb <= a.tolerance) {  // :552-554
+      finished = true;
+      split_pos = st;
+      weight_left = wl;
+      left_alive = below_nonempty || !left_empty;
+      right_alive = true;
+      break;
+    }
+    if (O::lt(wl, O::sub(sum, wl), q)) {  // :566-571
+      lo = st;
+      prev_side = SIDE_MIN;
+      w_below = wl;
+      below_nonempty = below_nonempty || !left_empty;
+      t = R;
+    } else {
+      hi = st;
+      hi_incl = 0;
+      prev_side = SIDE_MAX;
+      min_above = right_min;
+      t = L;
+    }
+  }
+  ns.iters = iters;
+  if (!finished) {
+    ns.lo = lo; ns.hi = hi;
+    ns.w_below = w_below;
+    ns.min_above = min_above;
+    ns.prev_side = (uint8_t)prev_side;
+    ns.hi_incl = (uint8_t)hi_incl;
+    ns.below_nonempty = (uint8_t)below_nonempty;
+    ns.done = 0;
+    a.rtable[p] = make_float4(lo, hi, hi_incl ? 1.f : 0.f, 0.f);
+    atomicAdd(&a.gp->unresolved, 1u);
+    return;
+  }
+  ns.done = 1;
+  a.rtable[p] = make_float4(1.f, 0.f, 0.f, 0.f);
+  a.table_next[p] = make_float4(split_pos, ns.box_lo[next_axis], ns.box_hi[next_axis], 0.f);
+  if (a.trace.visited) {
+    a.trace.visited[heap] = 1;
+    a.trace.split_pos[heap] = split_pos;
+    a.trace.weight_left[heap] = O::f64(weight_left, q);
+    a.trace.sum[heap] = O::f64(sum, q);
+    a.trace.iters[heap] = iters;
+  }
+  if (!a.last_level) {  // :613-616 and the arguments of the two recursive calls
+    NodeState cl, cr;
+    for (int d = 0; d < 3; ++d) {
+      cl.box_lo[d] = cr.box_lo[d] = ns.box_lo[d];
+      cl.box_hi[d] = cr.box_hi[d] = ns.box_hi[d];
+    }
+    cl.box_hi[axis] = split_pos;
+    cr.box_lo[axis] = split_pos;
+    cl.sum = weight_left;
+    cr.sum = O::sub(sum, weight_left);
+    cl.w_below = cr.w_below = 0;
+    cl.lo = cr.lo = 0.f;
+    cl.hi = cr.hi = 0.f;
+    cl.min_above = cr.min_above = KEY_EMPTY;
+    cl.iters = cr.iters = 0;
+    cl.alive = left_alive;
+    cr.alive = right_alive;
+    cl.done = cr.done = 0;
+    cl.prev_side = cr.prev_side = SIDE_NONE;
+    cl.hi_incl = cr.hi_incl = 1;
+    cl.below_nonempty = cr.below_nonempty = 0;
+    for (int d = 0; d < 3; ++d) cl.pad[d] = cr.pad[d] = 0;
+    a.next[2 * p] = cl;
+    a.next[2 * p + 1] = cr;
+  } else {
+    if (left_alive) atomicMin(&a.gp->leaf_min, 2 * p);
+    if (right_alive) atomicMin(&a.gp->leaf_min, 2 * p + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Final ids: last child choice, minus the smallest id present (:698-702).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+emit_kernel(size_t n, const uint32_t *__restrict__ ids, const float *__restrict__ xp,
+            const float4 *__restrict__ table, int levels, const GlobalParams *__restrict__ gp,
+            unsigned long long *__restrict__ out, int out_vec) {
+  const uint32_t off = gp->leaf_min;
+  const size_t ngroups = (n + 3) / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint32_t pmask = (1u << (levels - 1)) - 1;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const size_t i0 = g * 4;
+    uint32_t pp[4] = {0, 0, 0, 0};
+    if (levels >= 2) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(ids + i0));
+      pp[0] = v.x; pp[1] = v.y; pp[2] = v.z; pp[3] = v.w;
+    }
+    const float4 xv = __ldcs(reinterpret_cast<const float4 *>(xp + i0));
+    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+    unsigned long long r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float split = __ldg(&table[pp[j] & pmask]).x;
+      r[j] = (unsigned long long)(2 * pp[j] + (!(x[j] < split) ? 1u : 0u) - off);
+    }
+    if (i0 + 4 <= n && out_vec) {
+      __stcs(reinterpret_cast<ulonglong2 *>(out + i0), make_ulonglong2(r[0], r[1]));
+      __stcs(reinterpret_cast<ulonglong2 *>(out + i0) + 1, make_ulonglong2(r[2], r[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i0 + j < n) out[i0 + j] = r[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// RIB moments (geometry.rs:273-284): coordinate sums, then the scatter matrix
+// about the centroid.  f64; per-block partial sums are combined in block order
+// by moments_final_kernel so the result does not depend on scheduling.
+// ---------------------------------------------------------------------------
+template <int D, bool SCATTER>
+__global__ void __launch_bounds__(256)
+moments_partial_kernel(const double *__restrict__ pts, size_t n, double *partial, double c0,
+                       double c1, double c2) {
+  constexpr int NV = SCATTER ? D * D : D;
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  const double c[3] = {c0, c1, c2};
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double p[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) p[d] = __ldcs(pts + i * D + d);
+    if (SCATTER) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) p[d] = __dsub_rn(p[d], c[d]);
+#pragma unroll
+      for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int s = 0; s < D; ++s)
+          acc[r * D + s] = __dadd_rn(acc[r * D + s], __dmul_rn(p[r], p[s]));
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = __dadd_rn(acc[d], p[d]);
+    }
+  }
+  __shared__ double s_acc[8][NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double t = acc[v];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+    if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5][v] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += s_acc[wv][threadIdx.x];
+    partial[blockIdx.x * 16 + threadIdx.x] = t;
+  }
+}
+
+__global__ void moments_final_kernel(const double *partial, int nblocks, int nv, double *out) {
+  const int v = threadIdx.x;
+  if (v >= nv) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += partial[b * 16 + v];
+  out[v] = t;
+}
+
+}  // namespace cb

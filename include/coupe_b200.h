@@ -1,0 +1,104 @@
+/*
+ * coupe_b200.h — device-level C ABI of the B200 RCB/RIB engine.
+ *
+ * coupe.h (the reference-compatible boundary) is implemented on top of these
+ * entry points; they are exported so that a host that already keeps its mesh
+ * on the GPU (or a benchmark that wants the H2D/D2H copies outside the timed
+ * region) can call the same CUDA path with DEVICE pointers.  Plain pointers
+ * and sizes only; streams are passed as `void *` (a cudaStream_t).
+ *
+ * What each call replaces in the reference (coupe/src/algorithms/
+ * recursive_bisection.rs): coupe_b200_rcb_device = rcb() :644-705 with
+ * rcb_recurse :575-642 and par_rcb_split :456-573; coupe_b200_rib_device =
+ * rib() :829-851 with OrientedBoundingBox::from_points (geometry.rs:210-228).
+ */
+#ifndef COUPE_B200_H
+#define COUPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct coupe_b200_ctx coupe_b200_ctx;
+
+/* Weight descriptions accepted by the device entry points. */
+enum coupe_b200_wtype {
+	COUPE_B200_W_I32 = 0, /* same values as enum coupe_type */
+	COUPE_B200_W_I64 = 1,
+	COUPE_B200_W_F64 = 2,
+};
+
+/* Counters of the last call on a context (all ranks hold the same values
+ * except the *_local ones). */
+typedef struct coupe_b200_stats {
+	uint64_t n_local;        /* points on this rank */
+	uint64_t n_global;       /* points over all ranks */
+	uint32_t levels;         /* iter_count */
+	uint32_t dense_sweeps;   /* first passes (one per level) */
+	uint32_t refine_sweeps;  /* sparse refinement passes */
+	uint32_t kernel_launches;/* CUDA kernels launched by the call */
+	uint32_t collectives;    /* NCCL calls issued by the call */
+	int32_t  weight_shift;   /* fixed-point shift used for f64 weights */
+	uint32_t host_syncs;     /* stream synchronisations inside the call */
+	uint32_t reserved;
+	double   matrix[9];      /* RIB: the obb_to_aabb matrix applied (row-major DxD) */
+} coupe_b200_stats;
+
+/* One context per process and GPU.  `device` is a CUDA ordinal.  Returns a
+ * coupe_err value. */
+int coupe_b200_ctx_create(coupe_b200_ctx **out, int device);
+void coupe_b200_ctx_destroy(coupe_b200_ctx *ctx);
+
+/* Multi-GPU: rank 0 calls coupe_b200_nccl_unique_id (128 bytes out), the host
+ * framework broadcasts the bytes (torch.distributed), every rank then calls
+ * coupe_b200_ctx_init_comm.  Points are sharded by the caller; each rank
+ * passes its own shard to the calls below and receives ids for its shard. */
+int coupe_b200_nccl_unique_id(void *out128);
+int coupe_b200_ctx_init_comm(coupe_b200_ctx *ctx, const void *unique_id128, int rank, int world);
+
+/*
+ * RCB on device-resident data.
+ *   part_dev     n uint64 part ids (device), written
+ *   points_dev   n*dim doubles, AoS (device)
+ *   weights_dev  n weights of `wtype` (device), or NULL for a constant weight
+ *   wconst_host  when weights_dev is NULL: host pointer to ONE value of `wtype`
+ * Returns a coupe_err value.  The call is synchronous with respect to the
+ * host only at its end (the stream is synchronised before returning).
+ */
+int coupe_b200_rcb_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev, uintptr_t dim,
+		uintptr_t n, const double *points_dev, int wtype, const void *weights_dev,
+		const void *wconst_host, uintptr_t iter_count, double tolerance);
+
+int coupe_b200_rib_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev, uintptr_t dim,
+		uintptr_t n, const double *points_dev, int wtype, const void *weights_dev,
+		const void *wconst_host, uintptr_t iter_count, double tolerance);
+
+/* Counters of the last call. */
+int coupe_b200_last_stats(const coupe_b200_ctx *ctx, coupe_b200_stats *out);
+
+/*
+ * Split tree of the last call, heap order (root 0, children 2i+1 / 2i+2),
+ * 2^iter_count - 1 entries each, copied to HOST arrays (any may be NULL):
+ * visited flag, f32 split position, left weight and node weight converted to
+ * f64 the way the bisection compared them, bisection iterations.
+ */
+int coupe_b200_last_trace(coupe_b200_ctx *ctx, uint8_t *visited, float *split_pos,
+		double *weight_left, double *sum, uint32_t *iters);
+
+/* Pre-size the context's scratch buffers for shards of up to n points so that
+ * later calls do not allocate. */
+int coupe_b200_reserve(coupe_b200_ctx *ctx, uintptr_t n, uintptr_t dim, uintptr_t iter_count);
+
+/* Tuning knobs for experiments (bench/profiles); safe defaults otherwise. */
+int coupe_b200_set_option(coupe_b200_ctx *ctx, const char *name, int64_t value);
+
+/* Library / build identification string. */
+const char *coupe_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

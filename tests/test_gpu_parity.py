@@ -1,0 +1,343 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+on the same seeded inputs.  Bit-exact part ids for integer weights and for f64
+weights accumulated in the documented fixed point; split positions identical;
+1e-9 relative agreement with the oracle's native f64 sums."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def cb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import coupe_b200
+
+    return coupe_b200
+
+
+def gen_points(rng, n, dim, kind):
+    if kind == "uniform":
+        return rng.random((n, dim))
+    if kind == "gauss":
+        return rng.normal(size=(n, dim)) * rng.uniform(0.1, 3.0, size=dim) + rng.normal(size=dim)
+    if kind == "cluster":
+        k = 5
+        c = rng.random((k, dim)) * 10 - 5
+        s = rng.uniform(0.01, 0.5, k)
+        j = rng.integers(0, k, n)
+        return c[j] + rng.normal(size=(n, dim)) * s[j, None]
+    if kind == "grid":  # structured mesh barycentres: heavy duplication per axis
+        m = max(2, int(round(n ** (1.0 / dim))))
+        idx = rng.integers(0, m, size=(n, dim))
+        return idx.astype(np.float64) + 0.5
+    if kind == "negative":  # brackets far from zero and spanning zero
+        return rng.random((n, dim)) * np.array([100.0, 1e-3, 7.0])[:dim] - np.array([99.0, 5e-4, 3.0])[:dim]
+    raise ValueError(kind)
+
+
+def gen_weights(rng, n, kind):
+    if kind == "i32":
+        return rng.integers(1, 100, n).astype(np.int32)
+    if kind == "i64":
+        return rng.integers(0, 10**9, n).astype(np.int64)
+    if kind == "i64neg":
+        return rng.integers(-50, 100, n).astype(np.int64)
+    if kind == "f64int":
+        return rng.integers(1, 50, n).astype(np.float64)
+    if kind == "f64":
+        return rng.uniform(0.5, 1.5, n)
+    if kind == "const_i32":
+        return np.array(1, dtype=np.int32)
+    if kind == "const_f64":
+        return np.array(1.0, dtype=np.float64)
+    if kind == "const_f64_odd":
+        return np.array(0.3, dtype=np.float64)
+    raise ValueError(kind)
+
+
+def run_device(cb, pts, w, iters, tol, rib=False, ctx=None):
+    dev = torch.device("cuda", 0)
+    tp = torch.from_numpy(np.ascontiguousarray(pts)).to(dev)
+    tw = torch.from_numpy(w).to(dev) if w.ndim else w
+    part = torch.full((pts.shape[0],), -1, dtype=torch.int64, device=dev)
+    algo = (cb.Rib if rib else cb.Rcb)(iter_count=iters, tolerance=tol, context=ctx)
+    algo.partition(part, (tp, tw))
+    torch.cuda.synchronize()
+    return part.cpu().numpy().astype(np.uint64)
+
+
+def run_host(cb, pts, w, iters, tol, rib=False):
+    part = np.full(pts.shape[0], 2**63, dtype=np.uint64)
+    (cb.Rib if rib else cb.Rcb)(iter_count=iters, tolerance=tol).partition(part, (pts, w))
+    return part
+
+
+# ---- the reference's own known answers, through the reference-compatible C ABI ----
+
+def test_reference_known_answers_through_c_abi(cb):
+    pts = np.array([[-1.3, 6.0], [2.0, -4.0], [1.0, 1.0], [-3.0, -2.5],
+                    [-1.3, -0.3], [2.0, 1.0], [-3.0, 1.0], [1.3, -2.0]])
+    p = run_host(cb, pts, np.ones(8), 2, 0.05)  # recursive_bisection.rs:1077-1115
+    assert p.tolist() == [1, 2, 3, 0, 0, 3, 1, 2]
+    pts = np.array([[1.0, 1.0], [-1.0, 1.0], [1.0, -1.0], [-1.0, -1.0]])
+    p = run_host(cb, pts, np.ones(4, dtype=np.int32), 2, 0.0)  # doctest :739-768
+    assert p.tolist() == [3, 1, 2, 0]
+    sq = np.array([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 1.0]])  # coupe-ffi/examples/rcb.c
+    one = np.array(1, dtype=np.int32)
+    assert run_host(cb, sq, one, 1, 0.05).tolist() == [0, 0, 1, 1]
+    assert run_host(cb, sq, one, 2, 0.05).tolist() == [0, 1, 2, 3]
+    rp = np.array([[1.0, 10.0], [-1.0, 10.0], [1.0, -10.0], [-1.0, -10.0]])
+    p = run_host(cb, rp, np.ones(4, dtype=np.int32), 1, 0.0, rib=True)  # doctest :864-893
+    assert p[0] == p[1] and p[2] == p[3] and p[1] != p[2]
+
+
+def test_c_abi_errors(cb):
+    from coupe_b200 import _lib
+
+    L = _lib.lib()
+    pts = np.zeros((4, 2))
+    w = np.ones(3, dtype=np.int64)
+    part = np.zeros(4, dtype=np.uint64)
+    dp = L.coupe_data_array(4, 2, pts.ctypes.data)
+    dw = L.coupe_data_array(3, 1, w.ctypes.data)
+    assert L.coupe_rcb(part.ctypes.data, 2, dp, dw, 1, 0.05) == 6  # LEN_MISMATCH
+    L.coupe_data_free(dw)
+    dw = L.coupe_data_array(4, 1, np.ones(4, dtype=np.int64).ctypes.data)
+    assert L.coupe_rcb(part.ctypes.data, 4, dp, dw, 1, 0.05) == 3  # BAD_DIMENSION
+    assert L.coupe_rib(part.ctypes.data, 1, dp, dw, 1, 0.05) == 3
+    L.coupe_data_free(dp)
+    L.coupe_data_free(dw)
+    L.coupe_data_free(None)
+    with pytest.raises(cb.InputLenMismatch):
+        cb.Rcb(2, 0.05).partition(part, (pts, w))
+
+
+def test_c_abi_data_fn_and_constant(cb, oracle):
+    from coupe_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(1)
+    n = 100_003
+    pts = rng.random((n, 3))
+    w = rng.integers(1, 9, n).astype(np.int64)
+    want = oracle.rcb(pts, w, 5, 0.05)
+
+    @_lib.I_TH
+    def point_i(ctx, i):
+        return pts.ctypes.data + 24 * i
+
+    @_lib.I_TH
+    def weight_i(ctx, i):
+        return w.ctypes.data + 8 * i
+
+    dp = L.coupe_data_fn(None, n, 2, point_i)
+    dw = L.coupe_data_fn(None, n, 1, weight_i)
+    part = np.zeros(n, dtype=np.uint64)
+    assert L.coupe_rcb(part.ctypes.data, 3, dp, dw, 5, 0.05) == 0
+    assert np.array_equal(part, want)
+    L.coupe_data_free(dw)
+    two = np.array(2.0)
+    dw = L.coupe_data_constant(n, 2, two.ctypes.data)
+    assert L.coupe_rcb(part.ctypes.data, 3, dp, dw, 5, 0.05) == 0
+    assert np.array_equal(part, oracle.rcb(pts, two, 5, 0.05, mode=1))
+    L.coupe_data_free(dp)
+    L.coupe_data_free(dw)
+
+
+# ---- randomised parity against the oracle ----
+
+CASES = [
+    # n, dim, points, weights, iters, tol
+    (1, 2, "uniform", "i32", 3, 0.05),
+    (2, 3, "uniform", "i64", 2, 0.05),
+    (5, 2, "gauss", "const_i32", 4, 0.0),
+    (1023, 3, "uniform", "i64", 6, 0.05),
+    (4097, 2, "cluster", "i32", 7, 0.01),
+    (100_000, 3, "uniform", "const_f64", 10, 0.05),
+    (100_001, 2, "gauss", "i64", 12, 0.05),
+    (250_003, 3, "cluster", "f64int", 10, 0.001),
+    (200_000, 3, "grid", "i64", 9, 0.001),
+    (200_000, 2, "grid", "const_i32", 8, 0.0),
+    (300_000, 3, "negative", "i64neg", 8, 0.05),
+    (300_000, 3, "negative", "i32", 10, 0.0),
+    (1_000_000, 3, "uniform", "const_f64", 10, 0.05),
+    (1_000_003, 2, "uniform", "i64", 12, 0.05),
+    (500_000, 3, "gauss", "i64", 10, -1.0),
+    (50_000, 3, "cluster", "i64", 14, 0.05),
+    (20_000, 2, "uniform", "i32", 16, 0.05),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(map(str, c)))
+def test_rcb_bit_exact_integer_weights(cb, oracle, case):
+    n, dim, pk, wk, iters, tol = case
+    rng = np.random.default_rng(1000 + CASES.index(case))
+    pts = gen_points(rng, n, dim, pk)
+    w = gen_weights(rng, n, wk)
+    want, tr = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
+    got = run_device(cb, pts, w, iters, tol)
+    assert np.array_equal(got, want), f"{int((got != want).sum())} of {n} ids differ"
+    t = cb.default_context(0).trace(iters)
+    assert np.array_equal(t["visited"], tr.visited)
+    v = tr.visited.astype(bool)
+    assert np.array_equal(t["split_pos"][v], tr.split_pos[v])
+    assert np.array_equal(t["iters"][v], tr.iters[v])
+    assert np.array_equal(t["weight_left"][v], tr.weight_left[v])
+
+
+@pytest.mark.parametrize("n,dim,pk,iters,tol", [
+    (200_000, 3, "cluster", 10, 0.05),
+    (500_000, 3, "gauss", 10, 0.05),
+    (300_000, 2, "uniform", 12, 0.001),
+    (100_000, 3, "negative", 8, 0.0),
+])
+def test_rcb_f64_weights(cb, oracle, n, dim, pk, iters, tol):
+    rng = np.random.default_rng(n + dim + iters)
+    pts = gen_points(rng, n, dim, pk)
+    w = gen_weights(rng, n, "f64")
+    got = run_device(cb, pts, w, iters, tol)
+    t = cb.default_context(0).trace(iters)
+    # (1) bit-exact against the oracle run with the same fixed-point accumulation
+    want_fix, tr_fix = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
+    assert cb.default_context(0).stats()["weight_shift"] == tr_fix.shift
+    assert np.array_equal(got, want_fix)
+    assert np.array_equal(t["split_pos"], tr_fix.split_pos)
+    assert np.array_equal(t["weight_left"], tr_fix.weight_left)
+    # (2) against the oracle's native f64 sums: split positions identical here,
+    # left weights within 1e-9 relative (the north-star tolerance)
+    want_nat, tr_nat = oracle.rcb(pts, w, iters, tol, mode=0, trace=True)
+    v = tr_nat.visited.astype(bool)
+    np.testing.assert_allclose(t["split_pos"][v], tr_nat.split_pos[v], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(t["weight_left"][v], tr_nat.weight_left[v], rtol=1e-9, atol=0)
+    assert np.array_equal(got, want_nat)
+    nparts = 1 << iters
+    assert oracle.imbalance(nparts, got, w) == pytest.approx(oracle.imbalance(nparts, want_nat, w), rel=1e-9)
+
+
+def test_const_f64_non_dyadic_weight(cb, oracle):
+    rng = np.random.default_rng(4)
+    pts = gen_points(rng, 70_001, 3, "gauss")
+    w = gen_weights(rng, 0, "const_f64_odd")
+    assert np.array_equal(run_device(cb, pts, w, 9, 0.05), oracle.rcb(pts, w, 9, 0.05, mode=1))
+
+
+def test_edge_cases(cb, oracle):
+    dev = torch.device("cuda", 0)
+    # empty input: Ok(()), nothing written
+    part = torch.zeros(0, dtype=torch.int64, device=dev)
+    cb.Rcb(3, 0.05).partition(part, (torch.zeros((0, 2), dtype=torch.float64, device=dev),
+                                     torch.zeros(0, dtype=torch.int64, device=dev)))
+    # iter_count == 0: all zeros
+    pts = np.random.default_rng(0).random((1000, 3))
+    assert run_device(cb, pts, np.ones(1000, dtype=np.int64), 0, 0.05).tolist() == [0] * 1000
+    # all points identical
+    same = np.tile(np.array([[0.25, -3.0]]), (4001, 1))
+    w = np.ones(4001, dtype=np.int32)
+    assert np.array_equal(run_device(cb, same, w, 5, 0.05), oracle.rcb(same, w, 5, 0.05))
+    # zero total weight (imbalance is NaN)
+    z = np.zeros(1000, dtype=np.int64)
+    assert np.array_equal(run_device(cb, pts, z, 4, 0.05), oracle.rcb(pts, z, 4, 0.05))
+    # two distinct coordinates only
+    two = np.where(np.random.default_rng(1).random((5000, 2)) < 0.3, 1.0, 2.0)
+    w = np.random.default_rng(2).integers(1, 5, 5000).astype(np.int64)
+    assert np.array_equal(run_device(cb, two, w, 6, 0.05), oracle.rcb(two, w, 6, 0.05))
+    # length mismatch -> InputLenMismatch
+    with pytest.raises(cb.InputLenMismatch):
+        cb.Rcb(2, 0.05).partition(torch.zeros(10, dtype=torch.int64, device=dev),
+                                  (torch.zeros((10, 2), dtype=torch.float64, device=dev),
+                                   torch.zeros(9, dtype=torch.int64, device=dev)))
+    # unaligned weight pointer (slice of a larger tensor)
+    n = 10_001
+    pts = np.random.default_rng(3).random((n, 2))
+    w = np.random.default_rng(4).integers(1, 50, n + 1).astype(np.int32)
+    tw = torch.from_numpy(w).to(dev)[1:]
+    part = torch.zeros(n, dtype=torch.int64, device=dev)
+    cb.Rcb(7, 0.05).partition(part, (torch.from_numpy(pts).to(dev), tw))
+    assert np.array_equal(part.cpu().numpy().astype(np.uint64), oracle.rcb(pts, w[1:].copy(), 7, 0.05))
+
+
+@pytest.mark.parametrize("opts", [
+    {"force_global": 1},
+    {"nb_smem_log2": 8, "kmax_a": 2, "kmax_refine": 2},
+    {"kmax_a": 1, "kmax_refine": 1},
+    {"kmax_a": 3, "kmax_refine": 10},
+])
+def test_pass_schedules_do_not_change_results(cb, oracle, opts):
+    """Results must not depend on how many candidates a pass evaluates nor on the
+    accumulation path (shared-memory histograms vs L2 atomics)."""
+    ctx = cb.Context(0)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    rng = np.random.default_rng(77)
+    for pk, wk, dim, iters, tol in [("cluster", "i64", 3, 9, 0.0), ("grid", "i32", 2, 8, 0.001),
+                                    ("negative", "f64", 3, 7, 0.05)]:
+        pts = gen_points(rng, 60_001, dim, pk)
+        w = gen_weights(rng, 60_001, wk)
+        want, tr = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
+        got = run_device(cb, pts, w, iters, tol, ctx=ctx)
+        assert np.array_equal(got, want)
+        t = ctx.trace(iters)
+        assert np.array_equal(t["iters"], tr.iters)
+        assert np.array_equal(t["split_pos"], tr.split_pos)
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_rib_against_oracle(cb, oracle, dim):
+    rng = np.random.default_rng(dim)
+    n = 200_000
+    base = rng.normal(size=(n, dim)) * np.array([10.0, 1.0, 0.1])[:dim]
+    a = 0.6
+    rot = np.eye(dim)
+    rot[0, 0], rot[0, 1], rot[1, 0], rot[1, 1] = np.cos(a), -np.sin(a), np.sin(a), np.cos(a)
+    pts = base @ rot.T + 3.0
+    w = np.ones(n, dtype=np.int64)
+    want, mat = oracle.rib(pts, w, 6, 0.05, return_matrix=True)
+    got = run_device(cb, pts, w, 6, 0.05, rib=True)
+    got_mat = np.array(cb.default_context(0).stats()["matrix"][: dim * dim]).reshape(dim, dim)
+    # eigenvector / reflection agree to rounding (nalgebra's eigen solver is not pinned)
+    np.testing.assert_allclose(got_mat, mat, atol=1e-9)
+    # ids may differ only for points within rounding of a cut plane
+    assert (got != want).mean() < 1e-3
+    # RCB on the mapped points of THIS matrix must be bit-exact
+    mapped = np.empty_like(pts)
+    for r in range(dim):
+        acc = got_mat[r, 0] * pts[:, 0]
+        for s in range(1, dim):
+            acc = acc + got_mat[r, s] * pts[:, s]
+        mapped[:, r] = acc
+    assert np.array_equal(got, oracle.rcb(mapped, w, 6, 0.05))
+
+
+def test_large_size_properties(cb, oracle):
+    """Size-independent properties at a size the oracle does not run in a test:
+    every part is a box in (x, y, z) order statistics, ids dense in [0, 2^L),
+    and the partition is reproduced bit-for-bit by a second run."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    n, iters = 20_000_000, 10
+    pts = torch.rand((n, 3), dtype=torch.float64, device=dev, generator=g)
+    w = torch.randint(1, 100, (n,), dtype=torch.int64, device=dev, generator=g)
+    part = torch.empty(n, dtype=torch.int64, device=dev)
+    cb.Rcb(iters, 0.05).partition(part, (pts, w))
+    part2 = torch.empty_like(part)
+    cb.Rcb(iters, 0.05).partition(part2, (pts, w))
+    assert torch.equal(part, part2)
+    assert int(part.min()) == 0 and int(part.max()) == (1 << iters) - 1
+    loads = torch.zeros(1 << iters, dtype=torch.int64, device=dev).index_add_(0, part, w)
+    ideal = float(w.sum()) / (1 << iters)
+    assert float(loads.max()) / ideal - 1.0 < 0.5
+    # first split: ids < 512 lie strictly left of ids >= 512 along x
+    x = pts[:, 0].float()
+    left = part < (1 << (iters - 1))
+    assert float(x[left].max()) < float(x[~left].min())
+    # the trace's root split separates them
+    t = cb.default_context(0).trace(iters)
+    assert float(x[left].max()) < t["split_pos"][0] <= float(x[~left].min())
