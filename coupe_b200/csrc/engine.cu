@@ -190,14 +190,17 @@ struct coupe_b200_ctx {
   size_t max_smem = 0;
   std::mutex mu;
   // scratch
-  Buf xcols, ids, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, rtable, gp,
+  Buf xcols, ids, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
+      rtable, gp,
       tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
   uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   // options
-  int kmax_a = 8, nb_smem_log2 = 14, kmax_refine = 10, force_global = 0, trace_on = 1;
+  int kmax_a = 8, nb_smem_log2 = 14, kmax_refine = 10, force_global = 0, trace_on = 1, time_sweeps = 0;
+  std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
+  std::vector<int> event_kind;      // 0 dense, 1 refine
   // last call
   coupe_b200_stats stats{};
   uint32_t trace_levels = 0;
@@ -209,7 +212,7 @@ namespace {
 size_t sweep_smem_bytes(int level, int k, int copies_log2, bool table_in_smem) {
   const size_t nb = (size_t)1 << (level + k);
   size_t b = nb * ((size_t)1 << copies_log2) * 12;
-  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4);
+  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
   return b;
 }
 
@@ -237,6 +240,39 @@ void prepare_funcs(coupe_b200_ctx *c) {
   c->funcs_ready = true;
 }
 
+// How the dense first pass of a level is run.
+struct FirstPlan {
+  int k;               // bisection iterations resolved by the pass (2^k bins per node)
+  bool smem;           // block-private shared-memory histograms, else L2 atomics
+  int copies_log2;     // privatised copies per block (smem mode)
+  bool table_in_smem;  // per-parent table staged in shared memory
+  size_t bytes;        // dynamic shared memory
+};
+
+FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
+  FirstPlan p{};
+  p.k = std::min(c->kmax_a, c->nb_smem_log2 - level);
+  p.smem = !c->force_global && p.k >= 1;
+  p.table_in_smem = true;
+  if (p.smem) {
+    p.copies_log2 = std::min(5, c->nb_smem_log2 - (level + p.k));
+    p.bytes = sweep_smem_bytes(level, p.k, p.copies_log2, true);
+    if (p.bytes > c->max_smem) {
+      p.table_in_smem = false;
+      p.bytes = sweep_smem_bytes(level, p.k, p.copies_log2, false);
+    }
+    if (p.bytes > c->max_smem) p.smem = false;
+  }
+  if (!p.smem) {
+    p.k = std::max(1, std::min(c->kmax_a, 17 - level));
+    p.copies_log2 = 0;
+    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
+    p.table_in_smem = tb <= 64 * 1024;
+    p.bytes = p.table_in_smem ? tb : 0;
+  }
+  return p;
+}
+
 struct Run {
   coupe_b200_ctx *c;
   cudaStream_t st;
@@ -258,7 +294,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
              uintptr_t iter_count, double tolerance) {
   if (dim != 2 && dim != 3) return COUPE_ERR_BAD_DIMENSION;
   if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
-  if (!w_dev && !wconst_host) return COUPE_ERR_CRASH;
+  if (n > 0 && !w_dev && !wconst_host) return COUPE_ERR_CRASH;
   if (iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_CRASH;
   if (n >= ((uintptr_t)1 << 32) * 4) return COUPE_ERR_CRASH;
   CU(cudaSetDevice(c->device));
@@ -286,6 +322,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->nodes_b.ensure(max_nodes * sizeof(NodeState));
   c->table_a.ensure(max_nodes * sizeof(float4));
   c->table_b.ensure(max_nodes * sizeof(float4));
+  c->thi_a.ensure(max_nodes * sizeof(float));
+  c->thi_b.ensure(max_nodes * sizeof(float));
   c->rtable.ensure(max_nodes * sizeof(float4));
   c->gp.ensure(sizeof(GlobalParams));
   c->mom_partial.ensure((size_t)c->num_sms * 8 * 16 * sizeof(double));
@@ -308,13 +346,17 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
 
   // ---- global point count ---------------------------------------------------
   unsigned long long n_global = n;
-  if (c->world > 1) {
+  bool any_rank_has_array_weights = w_dev != nullptr;
+  if (c->world > 1) {  // a rank with an empty shard may not know whether weights are per point
     unsigned long long *d = reinterpret_cast<unsigned long long *>(c->hist_w.p);
-    CU(cudaMemcpyAsync(d, &n_global, 8, cudaMemcpyHostToDevice, st));
-    R.allreduce(d, 1, ncclUint64, ncclSum);
-    CU(cudaMemcpyAsync(c->h_pinned, d, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[2] = {n_global, w_dev ? 1ull : 0ull};
+    CU(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, st));
+    R.allreduce(d, 2, ncclUint64, ncclSum);
+    CU(cudaMemcpyAsync(c->h_pinned, d, 16, cudaMemcpyDeviceToHost, st));
     R.sync();
-    memcpy(&n_global, c->h_pinned, 8);
+    memcpy(h, c->h_pinned, 16);
+    n_global = h[0];
+    any_rank_has_array_weights = h[1] != 0;
   }
   S.n_global = n_global;
   if (n_global == 0) return COUPE_ERR_OK;  // BoundingBox::from_points -> None (:685-688)
@@ -385,17 +427,19 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   }
   long long wconst_i = 1;
   double wconst_f = 0.0;
-  const int w_is_const = w_dev == nullptr;
+  const int w_is_const = !any_rank_has_array_weights;
   if (w_is_const) {
+    if (!wconst_host) return COUPE_ERR_CRASH;
     if (wtype == WT_I32) wconst_i = *static_cast<const int *>(wconst_host);
     else if (wtype == WT_I64) wconst_i = *static_cast<const long long *>(wconst_host);
     else wconst_f = *static_cast<const double *>(wconst_host);
   }
   NodeState *cur = c->nodes_a.as<NodeState>(), *nxt = c->nodes_b.as<NodeState>();
   float4 *tab_cur = c->table_a.as<float4>(), *tab_next = c->table_b.as<float4>();
+  float *thi_cur = c->thi_a.as<float>(), *thi_next = c->thi_b.as<float>();
   float4 *rtable = c->rtable.as<float4>();
-  init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, D, wtype, w_is_const, wconst_i, wconst_f,
-                                    n_global);
+  init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, thi_cur, plan_first(c, 0).k, D, wtype,
+                                    w_is_const, wconst_i, wconst_f, n_global);
   R.launched();
 
   const int sweep_wt = w_is_const ? WT_CONST : wtype;
@@ -408,10 +452,27 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   uint32_t *hist_min = c->hist_min.as<uint32_t>();
   const int w_vec = ((uintptr_t)w_dev % 16) == 0;
 
+  size_t ev_used = 0;
+  c->event_kind.clear();
+  auto time_begin = [&](int kind) {
+    if (!c->time_sweeps) return;
+    while (c->events.size() < ev_used + 2) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      c->events.push_back(e);
+    }
+    c->event_kind.push_back(kind);
+    CU(cudaEventRecord(c->events[ev_used], st));
+  };
+  auto time_end = [&]() {
+    if (!c->time_sweeps) return;
+    CU(cudaEventRecord(c->events[ev_used + 1], st));
+    ev_used += 2;
+  };
   auto run_walk = [&](int level, int k, int first) {
     CU(cudaMemsetAsync(&gp->unresolved, 0, 4, st));
-    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, rtable, tr, tolerance,
-                level, k, D, first, level == L - 1, w_is_const};
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, rtable, tr, tolerance,
+                level, k, D, first, level == L - 1, w_is_const, plan_first(c, level + 1).k};
     const size_t bytes = ((size_t)2 << k) * 12;
     const int nodes = 1 << level;
     if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
@@ -426,26 +487,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   for (int level = 0; level < L; ++level) {
     const int axis = level % D, prev_axis = (level + D - 1) % D;
     // ---- dense first pass ----------------------------------------------------
-    int k = std::min(c->kmax_a, c->nb_smem_log2 - level);
-    bool smem = !c->force_global && k >= 1;
-    int copies_log2 = 0;
-    bool table_in_smem = true;
-    size_t bytes = 0;
-    if (smem) {
-      copies_log2 = std::min(5, c->nb_smem_log2 - (level + k));
-      bytes = sweep_smem_bytes(level, k, copies_log2, true);
-      if (bytes > c->max_smem) {
-        table_in_smem = false;
-        bytes = sweep_smem_bytes(level, k, copies_log2, false);
-      }
-      if (bytes > c->max_smem) smem = false;
-    }
-    if (!smem) {
-      k = std::max(1, std::min(c->kmax_a, 17 - level));
-      copies_log2 = 0;
-      table_in_smem = ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4) <= 64 * 1024;
-      bytes = table_in_smem ? ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4) : 0;
-    }
+    const FirstPlan plan = plan_first(c, level);
+    const int k = plan.k;
+    const bool smem = plan.smem;
+    const size_t bytes = plan.bytes;
     const uint32_t nb = 1u << (level + k);
     SweepArgs sa{};
     sa.n = n;
@@ -455,25 +500,28 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.w = w_dev;
     sa.gp = gp;
     sa.table = tab_cur;
+    sa.table_hi = thi_cur;
     sa.part_w = c->part_w.as<long long>();
     sa.part_min = c->part_min.as<uint32_t>();
     sa.hist_w = hist_w;
     sa.hist_min = hist_min;
     sa.level = level;
     sa.k = k;
-    sa.copies_log2 = copies_log2;
-    sa.table_in_smem = table_in_smem;
+    sa.copies_log2 = plan.copies_log2;
+    sa.table_in_smem = plan.table_in_smem;
     sa.w_vec = w_vec;
     if (!smem) {
       fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb);
       R.launched();
     }
+    time_begin(0);
     switch (sweep_wt) {
       case WT_I32: launch_sweep_first<WT_I32>(smem, sweep_grid, bytes, st, sa); break;
       case WT_I64: launch_sweep_first<WT_I64>(smem, sweep_grid, bytes, st, sa); break;
       case WT_F64: launch_sweep_first<WT_F64>(smem, sweep_grid, bytes, st, sa); break;
       default: launch_sweep_first<WT_CONST>(smem, sweep_grid, bytes, st, sa); break;
     }
+    time_end();
     R.launched();
     S.dense_sweeps += 1;
     if (smem) {
@@ -494,12 +542,14 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       fill_hist_kernel<<<(nbr + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nbr);
       R.launched();
       RefineArgs ra{n, x[axis], ids, w_dev, gp, rtable, hist_w, hist_min, level, kr};
+      time_begin(1);
       switch (sweep_wt) {
         case WT_I32: sweep_refine_kernel<WT_I32><<<refine_grid, 512, 0, st>>>(ra); break;
         case WT_I64: sweep_refine_kernel<WT_I64><<<refine_grid, 512, 0, st>>>(ra); break;
         case WT_F64: sweep_refine_kernel<WT_F64><<<refine_grid, 512, 0, st>>>(ra); break;
         default: sweep_refine_kernel<WT_CONST><<<refine_grid, 512, 0, st>>>(ra); break;
       }
+      time_end();
       R.launched();
       S.refine_sweeps += 1;
       R.allreduce(hist_w, nbr, ncclUint64, ncclSum);
@@ -508,6 +558,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     }
     std::swap(cur, nxt);
     std::swap(tab_cur, tab_next);
+    std::swap(thi_cur, thi_next);
   }
 
   // ---- final ids -------------------------------------------------------------
@@ -521,6 +572,11 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
   memcpy(&S.weight_shift, c->h_pinned, 4);
+  for (size_t e = 0; e + 1 < ev_used; e += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->events[e], c->events[e + 1]));
+    (c->event_kind[e / 2] ? S.refine_sweep_ms : S.dense_sweep_ms) += ms;
+  }
   CU(cudaGetLastError());
   return COUPE_ERR_OK;
 }
@@ -584,10 +640,11 @@ void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (Buf *b : {&c->xcols, &c->ids, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
-                 &c->nodes_b, &c->table_a, &c->table_b, &c->rtable, &c->gp, &c->tr_visited,
+                 &c->nodes_b, &c->table_a, &c->table_b, &c->thi_a, &c->thi_b, &c->rtable, &c->gp, &c->tr_visited,
                  &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
     b->release();
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   delete c;
 }
 
@@ -678,6 +735,7 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "kmax_refine") c->kmax_refine = (int)std::max<int64_t>(1, std::min<int64_t>(10, value));
   else if (s == "force_global") c->force_global = value != 0;
   else if (s == "trace") c->trace_on = value != 0;
+  else if (s == "time_sweeps") c->time_sweeps = value != 0;
   else return COUPE_ERR_NOT_FOUND;
   return COUPE_ERR_OK;
 }

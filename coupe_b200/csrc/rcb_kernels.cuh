@@ -79,6 +79,31 @@ __device__ __forceinline__ float midpoint_f32(float lo, float hi) {
   return __fmul_rn(__fadd_rn(lo, hi), 0.5f);
 }
 
+// Fast binning parameters of a bracket [lo, hi] split into 2^k dyadic bins.
+// The exact bin boundaries b_j come from k nested midpoint_f32 calls; each
+// rounding moves a boundary by at most ulp(M)/2, M = max(|lo|,|hi|), so
+// |b_j - (lo + W j / 2^k)| <= k/2 ulp(M) with W = hi - lo.  The sweep computes
+// t = fl(fl(x - lo) * inv), inv = fl(2^k / W): three roundings, |t - t_exact| <=
+// 3.01 * 2^(k-24).  If frac(t) is farther than eps = 1.5 (E + 4 * 2^(k-24)) from 0
+// and 1, with E = k/2 ulp(M) 2^k / W, then floor(t) IS the exact bin; otherwise
+// the point takes the exact k-step descend.  half_m_eps = 0.5 - eps; a negative
+// value disables the fast path for the node (narrow bracket far from zero).
+__device__ __forceinline__ void fast_bin_params(float lo, float hi, int k, float &inv,
+                                                float &half_m_eps) {
+  inv = 0.f;
+  half_m_eps = -1.f;
+  const double W = (double)hi - (double)lo;
+  const float M = fmaxf(fabsf(lo), fabsf(hi));
+  if (!(W > 0.0) || !(M < 3.0e38f)) return;
+  const double U = (double)nextafterf(M, 3.4e38f) - (double)M;
+  const double scale = ldexp(1.0, k) / W;
+  const double E = 0.5 * (double)k * U * scale;
+  const double eps = 1.5 * (E + 4.0 * ldexp(1.0, k - 24)) + 1e-6;
+  if (!(eps < 0.25) || !(scale < 1.0e37)) return;
+  inv = (float)scale;
+  half_m_eps = __double2float_rd(0.5 - eps);
+}
+
 // ---------------------------------------------------------------------------
 // Prologue: AoS f64 -> SoA f32 (round to nearest even), bounding box, max |w|.
 // ---------------------------------------------------------------------------
@@ -208,8 +233,9 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
 // ---------------------------------------------------------------------------
 // Root set-up once the (all-reduced) bounding box and max |w| are known.
 // ---------------------------------------------------------------------------
-__global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *table0, int D,
-                                 int wtype, int w_is_const, long long wconst_i, double wconst_f,
+__global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *table0,
+                                 float *table0_hi, int k0, int D, int wtype, int w_is_const,
+                                 long long wconst_i, double wconst_f,
                                  unsigned long long n_global) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   gp->n_global = n_global;
@@ -253,7 +279,10 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   ns.below_nonempty = 0;
   ns.pad[0] = ns.pad[1] = ns.pad[2] = 0;
   *root = ns;
-  table0[0] = make_float4(0.f, ns.box_lo[0], ns.box_hi[0], 0.f);
+  float inv, hme;
+  fast_bin_params(ns.box_lo[0], ns.box_hi[0], k0, inv, hme);
+  table0[0] = make_float4(0.f, ns.box_lo[0], inv, hme);
+  table0_hi[0] = ns.box_hi[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -317,7 +346,8 @@ struct SweepArgs {
   uint32_t *ids;            // in: parent path (level >= 2); out: path at this level (level >= 1)
   const void *w;            // weights (null for WT_CONST)
   const GlobalParams *gp;
-  const float4 *table;      // per parent: {parent split, bracket lo, bracket hi, -}
+  const float4 *table;      // per parent: {parent split, bracket lo, 2^k / width, 0.5 - eps}
+  const float *table_hi;    // per parent: bracket hi (exact descend only)
   long long *part_w;        // SMEM mode: per-block partial histograms [grid][nb]
   uint32_t *part_min;
   unsigned long long *hist_w;  // GLOBAL mode: histogram accumulated with L2 atomics
@@ -328,23 +358,48 @@ struct SweepArgs {
   int w_vec;                // weights are 16-byte aligned
 };
 
-// k dyadic bisection steps for four points at once: returns, per point, the
-// index of the leaf bracket the coordinate falls in (bit j of the path = went
-// right at depth j).  Identical arithmetic to the walk (midpoint_f32).
-__device__ __forceinline__ void descend4(const float (&x)[4], float (&lo)[4], float (&hi)[4],
-                                         int k, uint32_t (&bin)[4]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) bin[j] = 0;
+// Exact bin of x in the bracket [lo, hi]: k dyadic bisection steps with the
+// arithmetic of the walk (midpoint_f32); bit (k-1-s) of the result = went right
+// at depth s.
+__device__ __noinline__ uint32_t descend_exact(float x, float lo, float hi, int k) {
+  uint32_t bin = 0;
 #pragma unroll 1
   for (int s = 0; s < k; ++s) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float mid = midpoint_f32(lo[j], hi[j]);
-      const bool right = !(x[j] < mid);
-      bin[j] = (bin[j] << 1) | (right ? 1u : 0u);
-      lo[j] = right ? mid : lo[j];
-      hi[j] = right ? hi[j] : mid;
-    }
+    const float mid = midpoint_f32(lo, hi);
+    const bool right = !(x < mid);
+    bin = (bin << 1) | (right ? 1u : 0u);
+    lo = right ? mid : lo;
+    hi = right ? hi : mid;
+  }
+  return bin;
+}
+
+// Bin of x: one multiply + floor when x is provably away from every bin
+// boundary (fast_bin_params), the exact descend otherwise.
+__device__ __forceinline__ uint32_t bin_of(float x, float lo, float inv, float half_m_eps,
+                                           const float *hi_ptr, int k) {
+  const float t = __fmul_rn(__fsub_rn(x, lo), inv);
+  const float fl = floorf(t);
+  const float fr = __fsub_rn(t, fl);
+  if (fabsf(fr - 0.5f) < half_m_eps) return (uint32_t)(int)fl;
+  return descend_exact(x, lo, *hi_ptr, k);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void accumulate(uint32_t idx, long long w, uint32_t key, uint32_t *s_lo,
+                                           int32_t *s_hi, uint32_t *s_min,
+                                           unsigned long long *hist_w, uint32_t *hist_min) {
+  if (SMEM) {
+    // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
+    const uint32_t wlo = (uint32_t)w;
+    const uint32_t old = atomicAdd(&s_lo[idx], wlo);
+    int hinc = (int)(w >> 32);
+    if (old > ~wlo) ++hinc;  // carry out of the low word
+    if (hinc != 0) atomicAdd(&s_hi[idx], hinc);
+    if (key < s_min[idx]) atomicMin(&s_min[idx], key);
+  } else {
+    atomicAdd(&hist_w[idx], (unsigned long long)w);
+    if (key < __ldcg(&hist_min[idx])) atomicMin(&hist_min[idx], key);
   }
 }
 
@@ -354,11 +409,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const Swe
   const int k = a.k, level = a.level;
   const uint32_t nb = 1u << (level + k);  // bins of this level
   const int ncopy = 1 << a.copies_log2;
+  const size_t nacc = SMEM ? (size_t)nb * ncopy : 0;
   uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
-  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + (SMEM ? (size_t)nb * ncopy : 0));
-  uint32_t *s_min = reinterpret_cast<uint32_t *>(s_hi + (SMEM ? (size_t)nb * ncopy : 0));
-  float4 *s_table = reinterpret_cast<float4 *>(s_min + (SMEM ? (size_t)nb * ncopy : 0));
+  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + nacc);
+  uint32_t *s_min = reinterpret_cast<uint32_t *>(s_hi + nacc);
+  float4 *s_table = reinterpret_cast<float4 *>(s_min + nacc);
   const int nparents = 1 << (level > 0 ? level - 1 : 0);
+  float *s_table_hi = reinterpret_cast<float *>(s_table + nparents);
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i < nb * ncopy; i += blockDim.x) {
       s_lo[i] = 0;
@@ -367,16 +424,23 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const Swe
     }
   }
   if (a.table_in_smem)
-    for (int i = threadIdx.x; i < nparents; i += blockDim.x) s_table[i] = a.table[i];
+    for (int i = threadIdx.x; i < nparents; i += blockDim.x) {
+      s_table[i] = a.table[i];
+      s_table_hi[i] = a.table_hi[i];
+    }
   __syncthreads();
-  const float4 *table = a.table_in_smem ? s_table : a.table;
+  const bool tsm = a.table_in_smem != 0;
   const double scale = (WT == WT_F64) ? a.gp->scale : 1.0;
   const uint32_t copy_off = SMEM ? ((threadIdx.x >> 5) & (ncopy - 1)) * nb : 0;
+  uint32_t *c_lo = s_lo + copy_off;
+  int32_t *c_hi = s_hi + copy_off;
+  uint32_t *c_min = s_min + copy_off;
+  const uint32_t pmask = (uint32_t)nparents - 1;
 
   const size_t n = a.n;
-  const size_t ngroups = (n + 3) / 4;
+  const size_t nfull = n / 4;  // groups of four points without bounds checks
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < nfull; g += stride) {
     const size_t i0 = g * 4;
     uint32_t pp[4] = {0, 0, 0, 0};
     if (level >= 2) {
@@ -394,37 +458,35 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const Swe
       x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
     }
     long long w[4];
-    load_w4<WT>(a.w, i0, n, a.w_vec && (i0 + 4 <= n), scale, w);
+    load_w4<WT>(a.w, i0, n, a.w_vec != 0, scale, w);
 
-    uint32_t path[4];
-    float lo[4], hi[4];
-    const uint32_t pmask = (uint32_t)nparents - 1;
+    uint32_t path[4], bin[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 e = table[pp[j] & pmask];  // mask keeps padded lanes in range
+      const uint32_t pj = pp[j] & pmask;
+      const float4 e = tsm ? s_table[pj] : __ldg(&a.table[pj]);
       path[j] = level >= 1 ? 2 * pp[j] + (!(xp[j] < e.x) ? 1u : 0u) : 0u;
-      lo[j] = e.y;
-      hi[j] = e.z;
+      bin[j] = bin_of(x[j], e.y, e.z, e.w, tsm ? &s_table_hi[pj] : &a.table_hi[pj], k);
     }
     if (level >= 1)
       __stcs(reinterpret_cast<uint4 *>(a.ids + i0), make_uint4(path[0], path[1], path[2], path[3]));
-    uint32_t bin[4];
-    descend4(x, lo, hi, k, bin);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (i0 + j >= n) continue;
-      const uint32_t idx = (path[j] << k) + bin[j];
-      const uint32_t key = f2key(x[j]);
-      if (SMEM) {
-        const uint32_t wlo = (uint32_t)w[j];
-        const uint32_t old = atomicAdd(&s_lo[copy_off + idx], wlo);
-        const int hinc = (int)(w[j] >> 32) + ((uint32_t)(old + wlo) < old ? 1 : 0);
-        if (hinc != 0) atomicAdd(&s_hi[copy_off + idx], hinc);
-        if (key < s_min[copy_off + idx]) atomicMin(&s_min[copy_off + idx], key);
-      } else {
-        atomicAdd(&a.hist_w[idx], (unsigned long long)w[j]);
-        if (key < __ldcg(&a.hist_min[idx])) atomicMin(&a.hist_min[idx], key);
-      }
+    for (int j = 0; j < 4; ++j)
+      accumulate<SMEM>((path[j] << k) + bin[j], w[j], f2key(x[j]), c_lo, c_hi, c_min, a.hist_w,
+                       a.hist_min);
+  }
+  // tail: the last n % 4 points, one thread
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    for (size_t i = nfull * 4; i < n; ++i) {
+      const uint32_t pp = level >= 2 ? a.ids[i] : 0u;
+      const uint32_t pj = pp & pmask;
+      const float4 e = a.table[pj];
+      const uint32_t path = level >= 1 ? 2 * pp + (!(a.xp[i] < e.x) ? 1u : 0u) : 0u;
+      if (level >= 1) a.ids[i] = path;
+      const float x = a.x[i];
+      const uint32_t bin = descend_exact(x, e.y, a.table_hi[pj], k);
+      const long long w = load_w1<WT>(a.w, i, scale);
+      accumulate<SMEM>((path << k) + bin, w, f2key(x), c_lo, c_hi, c_min, a.hist_w, a.hist_min);
     }
   }
   if (SMEM) {
@@ -571,11 +633,13 @@ struct WalkArgs {
   const unsigned long long *hist_w;
   const uint32_t *hist_min;
   GlobalParams *gp;
-  float4 *table_next;        // per node: {split, lo, hi on the next axis, -}
+  float4 *table_next;        // per node: {split, lo, 2^k/width, 0.5-eps} on the next axis
+  float *table_next_hi;      // per node: hi on the next axis
   float4 *rtable;            // per node: refinement bracket
   Trace trace;
   double tolerance;
   int level, k, D, first, last_level, w_is_const;
+  int k_next;                // candidates per node of the next level's dense sweep
 };
 
 template <int WT>
@@ -594,7 +658,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     if (a.first && threadIdx.x == 0) {  // empty node: rcb_recurse returns at once (:586-588)
       ns.done = 1;
       a.rtable[p] = make_float4(1.f, 0.f, 0.f, 0.f);
-      a.table_next[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      a.table_next[p] = make_float4(0.f, 0.f, 0.f, -1.f);
+      a.table_next_hi[p] = 0.f;
       if (!a.last_level) {
         a.next[2 * p].alive = 0;
         a.next[2 * p + 1].alive = 0;
@@ -718,7 +783,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   }
   ns.done = 1;
   a.rtable[p] = make_float4(1.f, 0.f, 0.f, 0.f);
-  a.table_next[p] = make_float4(split_pos, ns.box_lo[next_axis], ns.box_hi[next_axis], 0.f);
+  {
+    float inv, hme;
+    fast_bin_params(ns.box_lo[next_axis], ns.box_hi[next_axis], a.k_next, inv, hme);
+    a.table_next[p] = make_float4(split_pos, ns.box_lo[next_axis], inv, hme);
+    a.table_next_hi[p] = ns.box_hi[next_axis];
+  }
   if (a.trace.visited) {
     a.trace.visited[heap] = 1;
     a.trace.split_pos[heap] = split_pos;

@@ -44,6 +44,8 @@ typedef struct coupe_b200_stats {
 	uint32_t host_syncs;     /* stream synchronisations inside the call */
 	uint32_t reserved;
 	double   matrix[9];      /* RIB: the obb_to_aabb matrix applied (row-major DxD) */
+	double   dense_sweep_ms; /* option "time_sweeps": summed device time of the dense sweeps */
+	double   refine_sweep_ms;/* option "time_sweeps": summed device time of the refinement sweeps */
 } coupe_b200_stats;
 
 /* One context per process and GPU.  `device` is a CUDA ordinal.  Returns a

@@ -207,8 +207,11 @@ def test_rcb_f64_weights(cb, oracle, n, dim, pk, iters, tol):
     want_fix, tr_fix = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
     assert cb.default_context(0).stats()["weight_shift"] == tr_fix.shift
     assert np.array_equal(got, want_fix)
-    assert np.array_equal(t["split_pos"], tr_fix.split_pos)
-    assert np.array_equal(t["weight_left"], tr_fix.weight_left)
+    assert np.array_equal(t["visited"], tr_fix.visited)
+    vf = tr_fix.visited.astype(bool)
+    assert np.array_equal(t["split_pos"][vf], tr_fix.split_pos[vf])
+    assert np.array_equal(t["weight_left"][vf], tr_fix.weight_left[vf])
+    assert np.array_equal(t["iters"][vf], tr_fix.iters[vf])
     # (2) against the oracle's native f64 sums: split positions identical here,
     # left weights within 1e-9 relative (the north-star tolerance)
     want_nat, tr_nat = oracle.rcb(pts, w, iters, tol, mode=0, trace=True)
@@ -283,8 +286,10 @@ def test_pass_schedules_do_not_change_results(cb, oracle, opts):
         got = run_device(cb, pts, w, iters, tol, ctx=ctx)
         assert np.array_equal(got, want)
         t = ctx.trace(iters)
-        assert np.array_equal(t["iters"], tr.iters)
-        assert np.array_equal(t["split_pos"], tr.split_pos)
+        v = tr.visited.astype(bool)
+        assert np.array_equal(t["visited"], tr.visited)
+        assert np.array_equal(t["iters"][v], tr.iters[v])
+        assert np.array_equal(t["split_pos"][v], tr.split_pos[v])
     ctx.close()
 
 
