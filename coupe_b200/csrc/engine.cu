@@ -190,8 +190,8 @@ struct coupe_b200_ctx {
   size_t max_smem = 0;
   std::mutex mu;
   // scratch
-  Buf xcols, ids, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
-      rtable, gp,
+  Buf xcols, ids, w32, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
+      tsp_a, tsp_b, target, rtable, gp,
       tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
   uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
   // comm
@@ -211,31 +211,57 @@ namespace {
 
 size_t sweep_smem_bytes(int level, int k, int copies_log2, bool table_in_smem) {
   const size_t nb = (size_t)1 << (level + k);
-  size_t b = nb * ((size_t)1 << copies_log2) * 12;
-  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
+  size_t b = (((nb + 1) * ((size_t)1 << copies_log2) * 12 + 15) / 16) * 16;
+  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4);
   return b;
 }
 
-template <int WT>
-void launch_sweep_first(bool smem, int grid, size_t bytes, cudaStream_t st, const SweepArgs &a) {
-  if (smem)
-    sweep_first_kernel<WT, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else
-    sweep_first_kernel<WT, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+template <int WIN, bool ROOT>
+void launch_sweep(bool smem, bool tsm, int grid, size_t bytes, cudaStream_t st, const SweepArgs &a) {
+  if (smem && tsm) sweep_kernel<WIN, true, ROOT, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else if (smem) sweep_kernel<WIN, true, ROOT, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else if (tsm) sweep_kernel<WIN, false, ROOT, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else sweep_kernel<WIN, false, ROOT, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+}
+
+void launch_sweep_any(int win, bool root, bool smem, bool tsm, int grid, size_t bytes, cudaStream_t st,
+                      const SweepArgs &a) {
+  if (root) {
+    switch (win) {
+      case WIN_I32: launch_sweep<WIN_I32, true>(smem, tsm, grid, bytes, st, a); break;
+      case WIN_I64: launch_sweep<WIN_I64, true>(smem, tsm, grid, bytes, st, a); break;
+      case WIN_F64: launch_sweep<WIN_F64, true>(smem, tsm, grid, bytes, st, a); break;
+      default: launch_sweep<WIN_CONST, true>(smem, tsm, grid, bytes, st, a); break;
+    }
+  } else {
+    switch (win) {
+      case WIN_I32: launch_sweep<WIN_I32, false>(smem, tsm, grid, bytes, st, a); break;
+      case WIN_I64: launch_sweep<WIN_I64, false>(smem, tsm, grid, bytes, st, a); break;
+      default: launch_sweep<WIN_CONST, false>(smem, tsm, grid, bytes, st, a); break;
+    }
+  }
 }
 
 void prepare_funcs(coupe_b200_ctx *c) {
   if (c->funcs_ready) return;
   const int m = (int)c->max_smem;
 #define SETATTR(fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, m))
-  SETATTR((sweep_first_kernel<WT_I32, true>));
-  SETATTR((sweep_first_kernel<WT_I64, true>));
-  SETATTR((sweep_first_kernel<WT_F64, true>));
-  SETATTR((sweep_first_kernel<WT_CONST, true>));
-  SETATTR((sweep_first_kernel<WT_I32, false>));
-  SETATTR((sweep_first_kernel<WT_I64, false>));
-  SETATTR((sweep_first_kernel<WT_F64, false>));
-  SETATTR((sweep_first_kernel<WT_CONST, false>));
+#define SETBOTH(win, root)                            \
+  SETATTR((sweep_kernel<win, true, root, true>));     \
+  SETATTR((sweep_kernel<win, true, root, false>));    \
+  SETATTR((sweep_kernel<win, false, root, true>));    \
+  SETATTR((sweep_kernel<win, false, root, false>))
+  SETBOTH(WIN_I32, true);
+  SETBOTH(WIN_I64, true);
+  SETBOTH(WIN_F64, true);
+  SETBOTH(WIN_CONST, true);
+  SETBOTH(WIN_I32, false);
+  SETBOTH(WIN_I64, false);
+  SETBOTH(WIN_CONST, false);
+  SETATTR((sweep_refine_kernel<WIN_I32>));
+  SETATTR((sweep_refine_kernel<WIN_I64>));
+  SETATTR((sweep_refine_kernel<WIN_CONST>));
+#undef SETBOTH
 #undef SETATTR
   c->funcs_ready = true;
 }
@@ -266,7 +292,7 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
   if (!p.smem) {
     p.k = std::max(1, std::min(c->kmax_a, 17 - level));
     p.copies_log2 = 0;
-    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
+    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4);
     p.table_in_smem = tb <= 64 * 1024;
     p.bytes = p.table_in_smem ? tb : 0;
   }
@@ -325,6 +351,11 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->thi_a.ensure(max_nodes * sizeof(float));
   c->thi_b.ensure(max_nodes * sizeof(float));
   c->rtable.ensure(max_nodes * sizeof(float4));
+  c->tsp_a.ensure(max_nodes * sizeof(float));
+  c->tsp_b.ensure(max_nodes * sizeof(float));
+  c->target.ensure(max_nodes * sizeof(uint32_t));
+  const bool narrow_w = w_dev && (wtype == WT_F64 || (wtype == WT_I64 && L > 1));
+  if (narrow_w) c->w32.ensure(npad * sizeof(int));
   c->gp.ensure(sizeof(GlobalParams));
   c->mom_partial.ensure((size_t)c->num_sms * 8 * 16 * sizeof(double));
   const size_t tr_n = L > 0 ? ((size_t)1 << L) - 1 : 1;
@@ -437,12 +468,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   NodeState *cur = c->nodes_a.as<NodeState>(), *nxt = c->nodes_b.as<NodeState>();
   float4 *tab_cur = c->table_a.as<float4>(), *tab_next = c->table_b.as<float4>();
   float *thi_cur = c->thi_a.as<float>(), *thi_next = c->thi_b.as<float>();
+  float *tsp_cur = c->tsp_a.as<float>(), *tsp_next = c->tsp_b.as<float>();
   float4 *rtable = c->rtable.as<float4>();
+  uint32_t *target = c->target.as<uint32_t>();
   init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, thi_cur, plan_first(c, 0).k, D, wtype,
                                     w_is_const, wconst_i, wconst_f, n_global);
   R.launched();
 
-  const int sweep_wt = w_is_const ? WT_CONST : wtype;
   const size_t ngroups = (n + 3) / 4;
   const int sweep_grid =
       std::max(1, (int)std::min<size_t>((size_t)c->num_sms, (ngroups + SWEEP_THREADS - 1) / SWEEP_THREADS));
@@ -450,7 +482,16 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
   unsigned long long *hist_w = c->hist_w.as<unsigned long long>();
   uint32_t *hist_min = c->hist_min.as<uint32_t>();
-  const int w_vec = ((uintptr_t)w_dev % 16) == 0;
+  int *w32 = narrow_w ? c->w32.as<int>() : nullptr;
+
+  // weight column read by the sweeps: the caller's array at the root level, the
+  // narrowed i32 copy afterwards when there is one
+  int win = WIN_CONST;
+  const void *wp = nullptr;
+  if (!w_is_const) {
+    win = wtype == WT_I32 ? WIN_I32 : wtype == WT_I64 ? WIN_I64 : WIN_F64;
+    wp = w_dev;
+  }
 
   size_t ev_used = 0;
   c->event_kind.clear();
@@ -469,69 +510,82 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     CU(cudaEventRecord(c->events[ev_used + 1], st));
     ev_used += 2;
   };
-  auto run_walk = [&](int level, int k, int first) {
+  uint32_t w_wide = 0;
+  auto run_walk = [&](int level, int k, int k0, int first) {
     CU(cudaMemsetAsync(&gp->unresolved, 0, 4, st));
-    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, rtable, tr, tolerance,
-                level, k, D, first, level == L - 1, w_is_const, plan_first(c, level + 1).k};
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, rtable, tr,
+                tolerance, level, k, D, first, level == L - 1, w_is_const, k0,
+                plan_first(c, level + 1).k};
     const size_t bytes = ((size_t)2 << k) * 12;
     const int nodes = 1 << level;
     if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     else if (wtype == WT_I64) walk_kernel<WT_I64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     R.launched();
-    CU(cudaMemcpyAsync(c->h_pinned, &gp->unresolved, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_pinned, &gp->unresolved, 8, cudaMemcpyDeviceToHost, st));
     R.sync();
+    w_wide = c->h_pinned[1];
     return c->h_pinned[0];
   };
 
+  int kprev = 0;
   for (int level = 0; level < L; ++level) {
     const int axis = level % D, prev_axis = (level + D - 1) % D;
     // ---- dense first pass ----------------------------------------------------
     const FirstPlan plan = plan_first(c, level);
     const int k = plan.k;
     const bool smem = plan.smem;
-    const size_t bytes = plan.bytes;
     const uint32_t nb = 1u << (level + k);
     SweepArgs sa{};
     sa.n = n;
     sa.x = x[axis];
     sa.xp = x[prev_axis];
-    sa.ids = ids;
-    sa.w = w_dev;
+    sa.idx = ids;
+    sa.w = wp;
+    sa.w32_out = level == 0 ? w32 : nullptr;
     sa.gp = gp;
     sa.table = tab_cur;
     sa.table_hi = thi_cur;
+    sa.table_split = tsp_cur;
     sa.part_w = c->part_w.as<long long>();
     sa.part_min = c->part_min.as<uint32_t>();
     sa.hist_w = hist_w;
     sa.hist_min = hist_min;
     sa.level = level;
     sa.k = k;
+    sa.kprev = kprev;
     sa.copies_log2 = plan.copies_log2;
     sa.table_in_smem = plan.table_in_smem;
-    sa.w_vec = w_vec;
+    sa.w_vec = ((uintptr_t)wp % 16) == 0;
     if (!smem) {
       fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb);
       R.launched();
     }
     time_begin(0);
-    switch (sweep_wt) {
-      case WT_I32: launch_sweep_first<WT_I32>(smem, sweep_grid, bytes, st, sa); break;
-      case WT_I64: launch_sweep_first<WT_I64>(smem, sweep_grid, bytes, st, sa); break;
-      case WT_F64: launch_sweep_first<WT_F64>(smem, sweep_grid, bytes, st, sa); break;
-      default: launch_sweep_first<WT_CONST>(smem, sweep_grid, bytes, st, sa); break;
-    }
+    launch_sweep_any(win, level == 0, smem, plan.table_in_smem, sweep_grid, plan.bytes, st, sa);
     time_end();
     R.launched();
     S.dense_sweeps += 1;
     if (smem) {
-      reduce_partials_kernel<<<(nb + 255) / 256, 256, 0, st>>>(sa.part_w, sa.part_min, sweep_grid, nb,
-                                                               hist_w, hist_min);
+      reduce_partials_kernel<<<(nb + 31) / 32, 256, 0, st>>>(sa.part_w, sa.part_min, sweep_grid, nb,
+                                                             hist_w, hist_min);
       R.launched();
     }
     R.allreduce(hist_w, nb, ncclUint64, ncclSum);
     R.allreduce(hist_min, nb, ncclUint32, ncclMin);
-    uint32_t unresolved = run_walk(level, k, 1);
+    uint32_t unresolved = run_walk(level, k, k, 1);
+    if (level == 0 && w32) {  // from here on the sweeps read the narrowed weights
+      if (c->world > 1 && wtype == WT_I64) {  // every rank must take the same path
+        R.allreduce(&gp->w_wide, 1, ncclUint32, ncclMax);
+        CU(cudaMemcpyAsync(c->h_pinned, &gp->w_wide, 4, cudaMemcpyDeviceToHost, st));
+        R.sync();
+        w_wide = c->h_pinned[0];
+      }
+      if (wtype == WT_F64 || !w_wide) {
+        win = WIN_I32;
+        wp = w32;
+      }
+    }
 
     // ---- sparse refinement passes while some bisection is undecided ----------
     int guard = 0;
@@ -541,30 +595,33 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       const uint32_t nbr = 1u << (level + kr);
       fill_hist_kernel<<<(nbr + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nbr);
       R.launched();
-      RefineArgs ra{n, x[axis], ids, w_dev, gp, rtable, hist_w, hist_min, level, kr};
+      const size_t tbytes = ((size_t)1 << level) * sizeof(uint32_t);
+      const int tsm = tbytes <= 96 * 1024;
+      RefineArgs ra{n, x[axis], ids, wp, gp, target, rtable, hist_w, hist_min, level, kr, k, tsm};
       time_begin(1);
-      switch (sweep_wt) {
-        case WT_I32: sweep_refine_kernel<WT_I32><<<refine_grid, 512, 0, st>>>(ra); break;
-        case WT_I64: sweep_refine_kernel<WT_I64><<<refine_grid, 512, 0, st>>>(ra); break;
-        case WT_F64: sweep_refine_kernel<WT_F64><<<refine_grid, 512, 0, st>>>(ra); break;
-        default: sweep_refine_kernel<WT_CONST><<<refine_grid, 512, 0, st>>>(ra); break;
+      switch (win) {
+        case WIN_I32: sweep_refine_kernel<WIN_I32><<<refine_grid, 512, tsm ? tbytes : 0, st>>>(ra); break;
+        case WIN_I64: sweep_refine_kernel<WIN_I64><<<refine_grid, 512, tsm ? tbytes : 0, st>>>(ra); break;
+        default: sweep_refine_kernel<WIN_CONST><<<refine_grid, 512, tsm ? tbytes : 0, st>>>(ra); break;
       }
       time_end();
       R.launched();
       S.refine_sweeps += 1;
       R.allreduce(hist_w, nbr, ncclUint64, ncclSum);
       R.allreduce(hist_min, nbr, ncclUint32, ncclMin);
-      unresolved = run_walk(level, kr, 0);
+      unresolved = run_walk(level, kr, k, 0);
     }
     std::swap(cur, nxt);
     std::swap(tab_cur, tab_next);
     std::swap(thi_cur, thi_next);
+    std::swap(tsp_cur, tsp_next);
+    kprev = k;
   }
 
   // ---- final ids -------------------------------------------------------------
   {
     const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
-    emit_kernel<<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, L, gp,
+    emit_kernel<<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, kprev, gp,
                                       reinterpret_cast<unsigned long long *>(part_dev),
                                       ((uintptr_t)part_dev % 16) == 0);
     R.launched();
@@ -639,7 +696,7 @@ void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (Buf *b : {&c->xcols, &c->ids, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
+  for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->tsp_a, &c->tsp_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
                  &c->nodes_b, &c->table_a, &c->table_b, &c->thi_a, &c->thi_b, &c->rtable, &c->gp, &c->tr_visited,
                  &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
     b->release();

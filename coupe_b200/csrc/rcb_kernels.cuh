@@ -4,7 +4,7 @@
 // reference (coupe/src/algorithms/recursive_bisection.rs):
 //   narrow_kernel       rcb() prologue :674-688  (f64 -> f32 SoA narrowing, root bbox,
 //                       geometry.rs:33-78) and, for RIB, the obb_to_aabb map (:848)
-//   sweep_first_kernel  the fold of par_rcb_split :478-520, for every candidate cut of
+//   sweep_kernel        the fold of par_rcb_split :478-520, for every candidate cut of
 //                       the next k bisection iterations of every node, fused with the
 //                       part-id update that reorder_split :122-181 + rcb_recurse
 //                       :618-641 perform by physically moving the points
@@ -35,12 +35,14 @@ struct NodeState {
   float lo, hi;                // current bisection bracket (min, max of the reference)
   uint32_t min_above;          // key of the smallest coordinate >= hi, KEY_EMPTY if none
   uint32_t iters;              // candidates evaluated so far
+  uint32_t sb;                 // dense-pass bin the bracket shrank to (refined nodes)
   uint8_t alive;               // node holds at least one point
   uint8_t done;                // split decided
   uint8_t prev_side;           // which bracket end the previous candidate became
   uint8_t hi_incl;             // hi is still the box bound (points == hi belong to the bracket)
   uint8_t below_nonempty;      // some point lies left of the bracket
   uint8_t pad[3];
+  uint32_t pad2;
 };
 
 // Device-resident scalars shared by the kernels of one call.
@@ -52,9 +54,9 @@ struct GlobalParams {
   long long wconst;                // constant weight in accumulator units
   uint32_t bbox_keys[8];           // [0..D) min keys, [4..4+D) inverted max keys
   uint32_t unresolved;             // nodes whose bisection needs another pass
+  uint32_t w_wide;                 // some i64 weight does not fit the narrowed i32 column
   uint32_t leaf_min;               // smallest non-empty leaf path
   int shift;
-  int pad;
 };
 
 struct Trace {
@@ -257,7 +259,7 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   gp->scale = ldexp(1.0, shift);
   gp->q = ldexp(1.0, -shift);
   long long wc = 1;
-  if (w_is_const) wc = wtype == WT_F64 ? __double2ll_rn(wconst_f * gp->scale) : wconst_i;
+  if (w_is_const) wc = wtype == WT_F64 ? (long long)__double2int_rn(wconst_f * gp->scale) : wconst_i;
   gp->wconst = wc;
   gp->unresolved = 0;
   gp->leaf_min = 0xFFFFFFFFu;
@@ -272,6 +274,8 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   ns.hi = ns.box_hi[0];
   ns.min_above = KEY_EMPTY;
   ns.iters = 0;
+  ns.sb = 0;
+  ns.pad2 = 0;
   ns.alive = n_global > 0;
   ns.done = 0;
   ns.prev_side = SIDE_NONE;
@@ -281,81 +285,64 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   *root = ns;
   float inv, hme;
   fast_bin_params(ns.box_lo[0], ns.box_hi[0], k0, inv, hme);
-  table0[0] = make_float4(0.f, ns.box_lo[0], inv, hme);
+  table0[0] = make_float4(ns.box_lo[0], inv, hme, 0.f);
   table0_hi[0] = ns.box_hi[0];
 }
 
 // ---------------------------------------------------------------------------
-// Weight loads: four consecutive weights in accumulator units.
+// Weight loads, in accumulator units.  WIN_* is the storage format a sweep
+// reads: the caller's i32 / i64 / f64 array, the engine's own narrowed i32
+// column (same format as the caller's i32), or nothing (constant weight).
 // ---------------------------------------------------------------------------
-template <int WT>
-__device__ __forceinline__ void load_w4(const void *__restrict__ w, size_t i0, size_t n, bool vec,
-                                        double scale, long long (&out)[4]) {
-  if (WT == WT_CONST) {
-    out[0] = out[1] = out[2] = out[3] = 1;
-  } else if (WT == WT_I32) {
-    const int *p = static_cast<const int *>(w);
-    if (vec) {
-      const int4 v = __ldcs(reinterpret_cast<const int4 *>(p + i0));
-      out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = (i0 + j < n) ? (long long)__ldcs(p + i0 + j) : 0;
-    }
-  } else if (WT == WT_I64) {
-    const long long *p = static_cast<const long long *>(w);
-    if (vec) {
-      const longlong2 a = __ldcs(reinterpret_cast<const longlong2 *>(p + i0));
-      const longlong2 b = __ldcs(reinterpret_cast<const longlong2 *>(p + i0) + 1);
-      out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = (i0 + j < n) ? __ldcs(p + i0 + j) : 0;
-    }
-  } else {
-    const double *p = static_cast<const double *>(w);
-    double t[4];
-    if (vec) {
-      const double2 a = __ldcs(reinterpret_cast<const double2 *>(p + i0));
-      const double2 b = __ldcs(reinterpret_cast<const double2 *>(p + i0) + 1);
-      t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = (i0 + j < n) ? __ldcs(p + i0 + j) : 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = __double2ll_rn(__dmul_rn(t[j], scale));
-  }
+enum : int { WIN_I32 = 0, WIN_I64 = 1, WIN_F64 = 2, WIN_CONST = 3 };
+
+// f64 weight -> fixed point: round to nearest even, saturating to the i32 range
+// (only a weight within 2^-32 (relative) below a power of two can saturate).
+__device__ __forceinline__ int quantise_f64(double w, double scale) {
+  return __double2int_rn(__dmul_rn(w, scale));
 }
 
-template <int WT>
+template <int WIN>
 __device__ __forceinline__ long long load_w1(const void *__restrict__ w, size_t i, double scale) {
-  if (WT == WT_CONST) return 1;
-  if (WT == WT_I32) return (long long)__ldcs(static_cast<const int *>(w) + i);
-  if (WT == WT_I64) return __ldcs(static_cast<const long long *>(w) + i);
-  return __double2ll_rn(__dmul_rn(__ldcs(static_cast<const double *>(w) + i), scale));
+  if (WIN == WIN_CONST) return 1;
+  if (WIN == WIN_I32) return (long long)__ldcs(static_cast<const int *>(w) + i);
+  if (WIN == WIN_I64) return __ldcs(static_cast<const long long *>(w) + i);
+  return (long long)quantise_f64(__ldcs(static_cast<const double *>(w) + i), scale);
 }
 
 // ---------------------------------------------------------------------------
-// Dense sweep: first pass of a level.
+// Dense sweep: the first pass of a level over every point.
+//
+// Per point the engine keeps ONE 32-bit word, idx = (node << k) + bin: the
+// node the point belongs to at this level and the dyadic bin of its
+// coordinate inside the node's bracket (k bisection steps).  idx is at the
+// same time the histogram slot of the point and all the next level needs to
+// find the child: a split decided within the first pass is a bin boundary, so
+// child = (bin >= split_bin); only points in the one bin a refined split fell
+// into compare their coordinate with the split position.
 // ---------------------------------------------------------------------------
+constexpr uint32_t SB_REFINED = 1u << 16;  // flag in the split-bin word of the parent table
+constexpr uint32_t TARGET_NONE = 0xFFFFFFFFu;
+
 struct SweepArgs {
   size_t n;
-  const float *x;           // coordinate on this level's axis
-  const float *xp;          // coordinate on the previous level's axis (level >= 1)
-  uint32_t *ids;            // in: parent path (level >= 2); out: path at this level (level >= 1)
-  const void *w;            // weights (null for WT_CONST)
-  const GlobalParams *gp;
-  const float4 *table;      // per parent: {parent split, bracket lo, 2^k / width, 0.5 - eps}
-  const float *table_hi;    // per parent: bracket hi (exact descend only)
-  long long *part_w;        // SMEM mode: per-block partial histograms [grid][nb]
+  const float *x;            // coordinate on this level's axis
+  const float *xp;           // coordinate on the previous level's axis (refined parents only)
+  uint32_t *idx;             // in: idx of the previous level (level >= 1); out: idx of this level
+  const void *w;             // weights in the kernel's WIN format (null for WIN_CONST)
+  int *w32_out;              // root level: narrowed i32 copy of i64 / f64 weights, or null
+  GlobalParams *gp;
+  const float4 *table;       // per parent: {bracket lo, 2^k / width, 0.5 - eps, split-bin word}
+  const float *table_hi;     // per parent: bracket hi (exact descend only)
+  const float *table_split;  // per parent: split position (refined parents only)
+  long long *part_w;         // SMEM mode: per-block partial histograms [grid][nb]
   uint32_t *part_min;
   unsigned long long *hist_w;  // GLOBAL mode: histogram accumulated with L2 atomics
   uint32_t *hist_min;
-  int level, k;
-  int copies_log2;          // SMEM mode: 2^copies_log2 privatised copies per block
+  int level, k, kprev;
+  int copies_log2;           // SMEM mode: 2^copies_log2 lane-private copies per block
   int table_in_smem;
-  int w_vec;                // weights are 16-byte aligned
+  int w_vec;                 // weights are 16-byte aligned
 };
 
 // Exact bin of x in the bracket [lo, hi]: k dyadic bisection steps with the
@@ -382,113 +369,197 @@ __device__ __forceinline__ uint32_t bin_of(float x, float lo, float inv, float h
   const float fl = floorf(t);
   const float fr = __fsub_rn(t, fl);
   if (fabsf(fr - 0.5f) < half_m_eps) return (uint32_t)(int)fl;
-  return descend_exact(x, lo, *hi_ptr, k);
+  return descend_exact(x, lo, __ldg(hi_ptr), k);
+}
+
+// Child (0 = left, 1 = right) of a point whose previous-level bin is b.
+__device__ __forceinline__ uint32_t child_of(uint32_t b, uint32_t sbword, const float *xp, size_t i,
+                                             const float *split_ptr) {
+  const uint32_t sb = sbword & 0xFFFFu;
+  uint32_t child = b >= sb ? 1u : 0u;
+  if ((sbword & SB_REFINED) && b == sb) child = !(__ldg(xp + i) < __ldg(split_ptr)) ? 1u : 0u;
+  return child;
 }
 
 template <bool SMEM>
-__device__ __forceinline__ void accumulate(uint32_t idx, long long w, uint32_t key, uint32_t *s_lo,
+__device__ __forceinline__ void accumulate(uint32_t slot, long long w, uint32_t key, uint32_t *s_lo,
                                            int32_t *s_hi, uint32_t *s_min,
                                            unsigned long long *hist_w, uint32_t *hist_min) {
   if (SMEM) {
     // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
     const uint32_t wlo = (uint32_t)w;
-    const uint32_t old = atomicAdd(&s_lo[idx], wlo);
+    const uint32_t old = atomicAdd(&s_lo[slot], wlo);
     int hinc = (int)(w >> 32);
     if (old > ~wlo) ++hinc;  // carry out of the low word
-    if (hinc != 0) atomicAdd(&s_hi[idx], hinc);
-    if (key < s_min[idx]) atomicMin(&s_min[idx], key);
+    if (hinc != 0) atomicAdd(&s_hi[slot], hinc);
+    if (key < s_min[slot]) atomicMin(&s_min[slot], key);
   } else {
-    atomicAdd(&hist_w[idx], (unsigned long long)w);
-    if (key < __ldcg(&hist_min[idx])) atomicMin(&hist_min[idx], key);
+    atomicAdd(&hist_w[slot], (unsigned long long)w);
+    if (key < __ldcg(&hist_min[slot])) atomicMin(&hist_min[slot], key);
   }
 }
 
-template <int WT, bool SMEM>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const SweepArgs a) {
+// Raw (unconverted) weight words of four consecutive points, so that the loads
+// of the next group can be in flight while the current one is processed.
+template <int WIN>
+struct RawW4 {};
+template <>
+struct RawW4<WIN_CONST> {
+  __device__ __forceinline__ void load(const void *, size_t, bool) {}
+  __device__ __forceinline__ void get(double, long long (&o)[4]) const { o[0] = o[1] = o[2] = o[3] = 1; }
+};
+template <>
+struct RawW4<WIN_I32> {
+  int4 v;
+  __device__ __forceinline__ void load(const void *w, size_t i0, bool vec) {
+    const int *p = static_cast<const int *>(w) + i0;
+    if (vec) v = __ldcs(reinterpret_cast<const int4 *>(p));
+    else v = make_int4(__ldcs(p), __ldcs(p + 1), __ldcs(p + 2), __ldcs(p + 3));
+  }
+  __device__ __forceinline__ void get(double, long long (&o)[4]) const {
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <>
+struct RawW4<WIN_I64> {
+  longlong2 a, b;
+  __device__ __forceinline__ void load(const void *w, size_t i0, bool vec) {
+    const long long *p = static_cast<const long long *>(w) + i0;
+    if (vec) {
+      a = __ldcs(reinterpret_cast<const longlong2 *>(p));
+      b = __ldcs(reinterpret_cast<const longlong2 *>(p) + 1);
+    } else {
+      a = make_longlong2(__ldcs(p), __ldcs(p + 1));
+      b = make_longlong2(__ldcs(p + 2), __ldcs(p + 3));
+    }
+  }
+  __device__ __forceinline__ void get(double, long long (&o)[4]) const {
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+};
+template <>
+struct RawW4<WIN_F64> {
+  double2 a, b;
+  __device__ __forceinline__ void load(const void *w, size_t i0, bool vec) {
+    const double *p = static_cast<const double *>(w) + i0;
+    if (vec) {
+      a = __ldcs(reinterpret_cast<const double2 *>(p));
+      b = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+    } else {
+      a = make_double2(__ldcs(p), __ldcs(p + 1));
+      b = make_double2(__ldcs(p + 2), __ldcs(p + 3));
+    }
+  }
+  __device__ __forceinline__ void get(double scale, long long (&o)[4]) const {
+    o[0] = quantise_f64(a.x, scale); o[1] = quantise_f64(a.y, scale);
+    o[2] = quantise_f64(b.x, scale); o[3] = quantise_f64(b.y, scale);
+  }
+};
+
+template <int WIN, bool ROOT>
+struct Group4 {  // everything the sweep reads for four consecutive points
+  uint4 pv;
+  float4 x;
+  RawW4<WIN> w;
+  __device__ __forceinline__ void load(const SweepArgs &a, size_t i0, bool vec) {
+    if (!ROOT) pv = __ldcs(reinterpret_cast<const uint4 *>(a.idx + i0));
+    else pv = make_uint4(0, 0, 0, 0);
+    x = __ldcs(reinterpret_cast<const float4 *>(a.x + i0));
+    w.load(a.w, i0, vec);
+  }
+};
+
+template <int WIN, bool SMEM, bool ROOT, bool TSM>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int k = a.k, level = a.level;
+  const int k = a.k, level = a.level, kprev = a.kprev;
   const uint32_t nb = 1u << (level + k);  // bins of this level
   const int ncopy = 1 << a.copies_log2;
-  const size_t nacc = SMEM ? (size_t)nb * ncopy : 0;
+  const uint32_t cstride = nb + 1;        // copies are skewed by one bank
+  const size_t nacc = SMEM ? (size_t)cstride * ncopy : 0;
   uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
   int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + nacc);
   uint32_t *s_min = reinterpret_cast<uint32_t *>(s_hi + nacc);
-  float4 *s_table = reinterpret_cast<float4 *>(s_min + nacc);
+  float4 *s_table = reinterpret_cast<float4 *>(smem_raw + ((nacc * 12 + 15) / 16) * 16);
   const int nparents = 1 << (level > 0 ? level - 1 : 0);
-  float *s_table_hi = reinterpret_cast<float *>(s_table + nparents);
   if (SMEM) {
-    for (uint32_t i = threadIdx.x; i < nb * ncopy; i += blockDim.x) {
+    const uint32_t total = cstride * (uint32_t)ncopy;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
       s_lo[i] = 0;
       s_hi[i] = 0;
       s_min[i] = KEY_EMPTY;
     }
   }
-  if (a.table_in_smem)
-    for (int i = threadIdx.x; i < nparents; i += blockDim.x) {
-      s_table[i] = a.table[i];
-      s_table_hi[i] = a.table_hi[i];
-    }
+  if (TSM)
+    for (int i = threadIdx.x; i < nparents; i += blockDim.x) s_table[i] = a.table[i];
   __syncthreads();
-  const bool tsm = a.table_in_smem != 0;
-  const double scale = (WT == WT_F64) ? a.gp->scale : 1.0;
-  const uint32_t copy_off = SMEM ? ((threadIdx.x >> 5) & (ncopy - 1)) * nb : 0;
+  const double scale = (WIN == WIN_F64) ? a.gp->scale : 1.0;
+  const uint32_t copy_off = SMEM ? (threadIdx.x & (ncopy - 1)) * cstride : 0;
   uint32_t *c_lo = s_lo + copy_off;
   int32_t *c_hi = s_hi + copy_off;
   uint32_t *c_min = s_min + copy_off;
-  const uint32_t pmask = (uint32_t)nparents - 1;
+  const uint32_t bmask = (1u << kprev) - 1;
+  const bool vec = a.w_vec != 0;
+  const bool narrow = ROOT && (WIN == WIN_I64 || WIN == WIN_F64) && a.w32_out != nullptr;
+  bool wide = false;  // some i64 weight does not fit the narrowed i32 column
 
   const size_t n = a.n;
   const size_t nfull = n / 4;  // groups of four points without bounds checks
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < nfull; g += stride) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Group4<WIN, ROOT> cur, nxt;
+  if (g < nfull) cur.load(a, g * 4, vec);
+  while (g < nfull) {
+    const size_t gn = g + stride;
+    if (gn < nfull) nxt.load(a, gn * 4, vec);  // in flight while this group is processed
     const size_t i0 = g * 4;
-    uint32_t pp[4] = {0, 0, 0, 0};
-    if (level >= 2) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(a.ids + i0));
-      pp[0] = v.x; pp[1] = v.y; pp[2] = v.z; pp[3] = v.w;
-    }
-    float xp[4] = {0.f, 0.f, 0.f, 0.f};
-    if (level >= 1) {
-      const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.xp + i0));
-      xp[0] = v.x; xp[1] = v.y; xp[2] = v.z; xp[3] = v.w;
-    }
-    float x[4];
-    {
-      const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.x + i0));
-      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-    }
+    const uint32_t pv[4] = {cur.pv.x, cur.pv.y, cur.pv.z, cur.pv.w};
+    const float x[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
     long long w[4];
-    load_w4<WT>(a.w, i0, n, a.w_vec != 0, scale, w);
-
-    uint32_t path[4], bin[4];
+    cur.w.get(scale, w);
+    uint32_t slot[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t pj = pp[j] & pmask;
-      const float4 e = tsm ? s_table[pj] : __ldg(&a.table[pj]);
-      path[j] = level >= 1 ? 2 * pp[j] + (!(xp[j] < e.x) ? 1u : 0u) : 0u;
-      bin[j] = bin_of(x[j], e.y, e.z, e.w, tsm ? &s_table_hi[pj] : &a.table_hi[pj], k);
+      const uint32_t p = pv[j] >> kprev;
+      const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
+      uint32_t node = 0;
+      if (!ROOT)
+        node = 2 * p + child_of(pv[j] & bmask, __float_as_uint(e.w), a.xp, i0 + j, a.table_split + p);
+      slot[j] = (node << k) + bin_of(x[j], e.x, e.y, e.z, a.table_hi + p, k);
     }
-    if (level >= 1)
-      __stcs(reinterpret_cast<uint4 *>(a.ids + i0), make_uint4(path[0], path[1], path[2], path[3]));
+    __stcs(reinterpret_cast<uint4 *>(a.idx + i0), make_uint4(slot[0], slot[1], slot[2], slot[3]));
+    if (narrow) {
+      __stcs(reinterpret_cast<int4 *>(a.w32_out + i0),
+             make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
+      if (WIN == WIN_I64)
+        wide = wide || w[0] != (int)w[0] || w[1] != (int)w[1] || w[2] != (int)w[2] || w[3] != (int)w[3];
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      accumulate<SMEM>((path[j] << k) + bin[j], w[j], f2key(x[j]), c_lo, c_hi, c_min, a.hist_w,
-                       a.hist_min);
+      accumulate<SMEM>(slot[j], w[j], f2key(x[j]), c_lo, c_hi, c_min, a.hist_w, a.hist_min);
+    cur = nxt;
+    g = gn;
   }
   // tail: the last n % 4 points, one thread
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
     for (size_t i = nfull * 4; i < n; ++i) {
-      const uint32_t pp = level >= 2 ? a.ids[i] : 0u;
-      const uint32_t pj = pp & pmask;
-      const float4 e = a.table[pj];
-      const uint32_t path = level >= 1 ? 2 * pp + (!(a.xp[i] < e.x) ? 1u : 0u) : 0u;
-      if (level >= 1) a.ids[i] = path;
+      const uint32_t pv = ROOT ? 0u : a.idx[i];
+      const uint32_t p = pv >> kprev;
+      const float4 e = a.table[p];
+      uint32_t node = 0;
+      if (!ROOT) node = 2 * p + child_of(pv & bmask, __float_as_uint(e.w), a.xp, i, a.table_split + p);
       const float x = a.x[i];
-      const uint32_t bin = descend_exact(x, e.y, a.table_hi[pj], k);
-      const long long w = load_w1<WT>(a.w, i, scale);
-      accumulate<SMEM>((path << k) + bin, w, f2key(x), c_lo, c_hi, c_min, a.hist_w, a.hist_min);
+      const uint32_t slot = (node << k) + descend_exact(x, e.x, a.table_hi[p], k);
+      a.idx[i] = slot;
+      const long long w = load_w1<WIN>(a.w, i, scale);
+      if (narrow) {
+        a.w32_out[i] = (int)w;
+        if (WIN == WIN_I64) wide = wide || w != (int)w;
+      }
+      accumulate<SMEM>(slot, w, f2key(x), c_lo, c_hi, c_min, a.hist_w, a.hist_min);
     }
   }
+  if (ROOT && WIN == WIN_I64 && wide) a.gp->w_wide = 1;
   if (SMEM) {
     __syncthreads();
     long long *pw = a.part_w + (size_t)blockIdx.x * nb;
@@ -497,8 +568,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const Swe
       unsigned long long acc = 0;
       uint32_t m = KEY_EMPTY;
       for (int c = 0; c < ncopy; ++c) {
-        acc += ((unsigned long long)(uint32_t)s_hi[c * nb + i] << 32) + s_lo[c * nb + i];
-        m = min(m, s_min[c * nb + i]);
+        const uint32_t s = c * cstride + i;
+        acc += ((unsigned long long)(uint32_t)s_hi[s] << 32) + s_lo[s];
+        m = min(m, s_min[s]);
       }
       pw[i] = (long long)acc;
       pm[i] = m;
@@ -506,21 +578,35 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_first_kernel(const Swe
   }
 }
 
-// Sum / min of the per-block partial histograms.
+// Sum / min of the per-block partial histograms: 32 bins x 8 slices of blocks
+// per thread block, so that even a 2^8-bin level keeps the SMs busy.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__restrict__ part_min,
                        int nblocks, uint32_t nb, unsigned long long *__restrict__ hist_w,
                        uint32_t *__restrict__ hist_min) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb) return;
+  __shared__ unsigned long long s_w[8][32];
+  __shared__ uint32_t s_m[8][32];
+  const uint32_t lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * 32 + lane;
   unsigned long long acc = 0;
   uint32_t m = KEY_EMPTY;
-  for (int b = 0; b < nblocks; ++b) {
-    acc += (unsigned long long)part_w[(size_t)b * nb + i];
-    m = min(m, part_min[(size_t)b * nb + i]);
+  if (i < nb)
+    for (int b = slice; b < nblocks; b += 8) {
+      acc += (unsigned long long)part_w[(size_t)b * nb + i];
+      m = min(m, part_min[(size_t)b * nb + i]);
+    }
+  s_w[slice][lane] = acc;
+  s_m[slice][lane] = m;
+  __syncthreads();
+  if (slice == 0 && i < nb) {
+#pragma unroll
+    for (int s = 1; s < 8; ++s) {
+      acc += s_w[s][lane];
+      m = min(m, s_m[s][lane]);
+    }
+    hist_w[i] = acc;
+    hist_min[i] = m;
   }
-  hist_w[i] = acc;
-  hist_min[i] = m;
 }
 
 __global__ void __launch_bounds__(256)
@@ -533,62 +619,59 @@ fill_hist_kernel(unsigned long long *hist_w, uint32_t *hist_min, uint32_t nb) {
 }
 
 // ---------------------------------------------------------------------------
-// Sparse sweep: only points inside the surviving bracket of an unresolved node
-// contribute (and only their weights are read).
+// Sparse sweep: only the points of the one first-pass bin an undecided
+// bisection narrowed down to contribute; every other point costs its 4-byte
+// idx word and nothing else.
 // ---------------------------------------------------------------------------
 struct RefineArgs {
   size_t n;
   const float *x;
-  const uint32_t *ids;     // path at this level (level >= 1)
+  const uint32_t *idx;     // idx of this level
   const void *w;
   const GlobalParams *gp;
-  const float4 *rtable;    // per node: {lo, hi, hi inclusive, -}; lo > hi when resolved
+  const uint32_t *target;  // per node: idx value of the bin under refinement, TARGET_NONE if resolved
+  const float4 *rtable;    // per node: {lo, hi, hi inclusive, -}
   unsigned long long *hist_w;
   uint32_t *hist_min;
-  int level, k;
+  int level, k, k0;        // k0: bins of the dense pass (idx = (node << k0) + bin)
+  int target_in_smem;
 };
 
-template <int WT>
+template <int WIN>
 __global__ void __launch_bounds__(512) sweep_refine_kernel(const RefineArgs a) {
-  const int k = a.k, level = a.level;
-  const double scale = (WT == WT_F64) ? a.gp->scale : 1.0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_target = reinterpret_cast<uint32_t *>(smem_raw);
+  const int k = a.k, k0 = a.k0;
+  const uint32_t nodes = 1u << a.level;
+  const bool tsm = a.target_in_smem != 0;
+  if (tsm) {
+    for (uint32_t i = threadIdx.x; i < nodes; i += blockDim.x) s_target[i] = a.target[i];
+    __syncthreads();
+  }
   const size_t n = a.n;
   const size_t ngroups = (n + 3) / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const uint32_t nmask = (1u << level) - 1;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
     const size_t i0 = g * 4;
-    uint32_t path[4] = {0, 0, 0, 0};
-    if (level >= 1) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(a.ids + i0));
-      path[0] = v.x; path[1] = v.y; path[2] = v.z; path[3] = v.w;
-    }
-    float x[4];
-    {
-      const float4 v = __ldcs(reinterpret_cast<const float4 *>(a.x + i0));
-      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-    }
+    const uint4 vv = __ldcs(reinterpret_cast<const uint4 *>(a.idx + i0));
+    const uint32_t v[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (i0 + j >= n) continue;
-      const uint32_t p = path[j] & nmask;
+      const uint32_t p = v[j] >> k0;
+      if (p >= nodes) continue;  // padding past n
+      if (v[j] != (tsm ? s_target[p] : __ldg(&a.target[p]))) continue;
+      const size_t i = i0 + j;
+      if (i >= n) continue;
+      const float x = __ldg(a.x + i);
       const float4 e = __ldg(&a.rtable[p]);
-      const bool in = !(x[j] < e.x) && (x[j] < e.y || (e.z != 0.f && x[j] <= e.y));
+      const bool in = !(x < e.x) && (x < e.y || (e.z != 0.f && x <= e.y));
       if (!in) continue;
-      float lo = e.x, hi = e.y;
-      uint32_t bin = 0;
-      for (int s = 0; s < k; ++s) {
-        const float mid = midpoint_f32(lo, hi);
-        const bool right = !(x[j] < mid);
-        bin = (bin << 1) | (right ? 1u : 0u);
-        lo = right ? mid : lo;
-        hi = right ? hi : mid;
-      }
-      const long long w = load_w1<WT>(a.w, i0 + j, scale);
-      const uint32_t idx = (p << k) + bin;
-      atomicAdd(&a.hist_w[idx], (unsigned long long)w);
-      const uint32_t key = f2key(x[j]);
-      if (key < __ldcg(&a.hist_min[idx])) atomicMin(&a.hist_min[idx], key);
+      const uint32_t bin = descend_exact(x, e.x, e.y, k);
+      const long long w = load_w1<WIN>(a.w, i, 1.0);
+      const uint32_t slot = (p << k) + bin;
+      atomicAdd(&a.hist_w[slot], (unsigned long long)w);
+      const uint32_t key = f2key(x);
+      if (key < __ldcg(&a.hist_min[slot])) atomicMin(&a.hist_min[slot], key);
     }
   }
 }
@@ -633,13 +716,16 @@ struct WalkArgs {
   const unsigned long long *hist_w;
   const uint32_t *hist_min;
   GlobalParams *gp;
-  float4 *table_next;        // per node: {split, lo, 2^k/width, 0.5-eps} on the next axis
+  float4 *table_next;        // per node: {lo, 2^k/width, 0.5-eps on the next axis, split-bin word}
   float *table_next_hi;      // per node: hi on the next axis
+  float *table_next_split;   // per node: split position on this axis
+  uint32_t *target;          // per node: idx value under refinement
   float4 *rtable;            // per node: refinement bracket
   Trace trace;
   double tolerance;
   int level, k, D, first, last_level, w_is_const;
-  int k_next;                // candidates per node of the next level's dense sweep
+  int k0;                    // bins of this level's dense pass
+  int k_next;                // bins of the next level's dense pass
 };
 
 template <int WT>
@@ -657,9 +743,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   if (a.first ? !ns.alive : ns.done) {
     if (a.first && threadIdx.x == 0) {  // empty node: rcb_recurse returns at once (:586-588)
       ns.done = 1;
-      a.rtable[p] = make_float4(1.f, 0.f, 0.f, 0.f);
-      a.table_next[p] = make_float4(0.f, 0.f, 0.f, -1.f);
+      a.target[p] = TARGET_NONE;
+      a.table_next[p] = make_float4(0.f, 0.f, -1.f, 0.f);
       a.table_next_hi[p] = 0.f;
+      a.table_next_split[p] = 0.f;
       if (!a.last_level) {
         a.next[2 * p].alive = 0;
         a.next[2 * p + 1].alive = 0;
@@ -716,6 +803,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   float split_pos = 0.f;
   long long weight_left = 0;
   bool left_alive = false, right_alive = false;
+  // split-bin word handed to the next level: first dense-pass bin on the right of the cut
+  uint32_t sbword = a.first ? 0u : (ns.sb | SB_REFINED);
   uint32_t t = 1;
   for (int depth = 0; depth < k; ++depth) {
     const float st = midpoint_f32(lo, hi);  // :472
@@ -735,6 +824,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
         weight_left = sum;
         left_alive = true;
         right_alive = false;
+        sbword = 1u << a.k0;  // every bin is on the left
         break;
       }
       hi = st;
@@ -752,6 +842,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
       weight_left = wl;
       left_alive = below_nonempty || !left_empty;
       right_alive = true;
+      if (a.first) sbword = (R << (k - depth - 1)) - nb;  // first leaf under R
       break;
     }
     if (O::lt(wl, O::sub(sum, wl), q)) {  // :566-571
@@ -777,17 +868,20 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     ns.hi_incl = (uint8_t)hi_incl;
     ns.below_nonempty = (uint8_t)below_nonempty;
     ns.done = 0;
+    if (a.first) ns.sb = t - nb;  // the dense-pass bin the bracket has shrunk to
+    a.target[p] = (p << a.k0) + ns.sb;
     a.rtable[p] = make_float4(lo, hi, hi_incl ? 1.f : 0.f, 0.f);
     atomicAdd(&a.gp->unresolved, 1u);
     return;
   }
   ns.done = 1;
-  a.rtable[p] = make_float4(1.f, 0.f, 0.f, 0.f);
+  a.target[p] = TARGET_NONE;
   {
     float inv, hme;
     fast_bin_params(ns.box_lo[next_axis], ns.box_hi[next_axis], a.k_next, inv, hme);
-    a.table_next[p] = make_float4(split_pos, ns.box_lo[next_axis], inv, hme);
+    a.table_next[p] = make_float4(ns.box_lo[next_axis], inv, hme, __uint_as_float(sbword));
     a.table_next_hi[p] = ns.box_hi[next_axis];
+    a.table_next_split[p] = split_pos;
   }
   if (a.trace.visited) {
     a.trace.visited[heap] = 1;
@@ -811,6 +905,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     cl.hi = cr.hi = 0.f;
     cl.min_above = cr.min_above = KEY_EMPTY;
     cl.iters = cr.iters = 0;
+    cl.sb = cr.sb = 0;
+    cl.pad2 = cr.pad2 = 0;
     cl.alive = left_alive;
     cr.alive = right_alive;
     cl.done = cr.done = 0;
@@ -830,27 +926,24 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
 // Final ids: last child choice, minus the smallest id present (:698-702).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-emit_kernel(size_t n, const uint32_t *__restrict__ ids, const float *__restrict__ xp,
-            const float4 *__restrict__ table, int levels, const GlobalParams *__restrict__ gp,
-            unsigned long long *__restrict__ out, int out_vec) {
+emit_kernel(size_t n, const uint32_t *__restrict__ idx, const float *__restrict__ xp,
+            const float4 *__restrict__ table, const float *__restrict__ table_split, int klast,
+            const GlobalParams *__restrict__ gp, unsigned long long *__restrict__ out, int out_vec) {
   const uint32_t off = gp->leaf_min;
   const size_t ngroups = (n + 3) / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const uint32_t pmask = (1u << (levels - 1)) - 1;
+  const uint32_t bmask = (1u << klast) - 1;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
     const size_t i0 = g * 4;
-    uint32_t pp[4] = {0, 0, 0, 0};
-    if (levels >= 2) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(ids + i0));
-      pp[0] = v.x; pp[1] = v.y; pp[2] = v.z; pp[3] = v.w;
-    }
-    const float4 xv = __ldcs(reinterpret_cast<const float4 *>(xp + i0));
-    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
-    unsigned long long r[4];
+    const uint4 vv = __ldcs(reinterpret_cast<const uint4 *>(idx + i0));
+    const uint32_t v[4] = {vv.x, vv.y, vv.z, vv.w};
+    unsigned long long r[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float split = __ldg(&table[pp[j] & pmask]).x;
-      r[j] = (unsigned long long)(2 * pp[j] + (!(x[j] < split) ? 1u : 0u) - off);
+      if (i0 + j >= n) continue;
+      const uint32_t p = v[j] >> klast;
+      const uint32_t sbword = __float_as_uint(__ldg(&table[p]).w);
+      r[j] = (unsigned long long)(2 * p + child_of(v[j] & bmask, sbword, xp, i0 + j, table_split + p) - off);
     }
     if (i0 + 4 <= n && out_vec) {
       __stcs(reinterpret_cast<ulonglong2 *>(out + i0), make_ulonglong2(r[0], r[1]));

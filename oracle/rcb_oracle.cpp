@@ -377,8 +377,10 @@ int rcb_dispatch(uint64_t *partition, size_t n, const double *pts, int wtype, co
     const int s = fix_shift(n, maxabs);
     if (shift_out) *shift_out = s;
     std::vector<int64_t> wv(n);
-    for (size_t i = 0; i < n; ++i)
-      wv[i] = (int64_t)std::llrint(std::ldexp(w_is_const ? src[0] : src[i], s));
+    for (size_t i = 0; i < n; ++i) {  // round to nearest even, saturating to the i32 range
+      const int64_t v = (int64_t)std::llrint(std::ldexp(w_is_const ? src[0] : src[i], s));
+      wv[i] = std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, v));
+    }
     rcb_run<PolFix, D>(PolFix{std::ldexp(1.0, -s)}, n, pts, wv, iter_count, tolerance, partition,
                        tr);
   } else {
