@@ -190,7 +190,7 @@ struct coupe_b200_ctx {
   size_t max_smem = 0;
   std::mutex mu;
   // scratch
-  Buf xcols, ids, w32, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
+  Buf xcols, ids, w32, node_rt, rfast, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
       tsp_a, tsp_b, target, rtable, gp,
       tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
   uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
@@ -212,56 +212,66 @@ namespace {
 size_t sweep_smem_bytes(int level, int k, int copies_log2, bool table_in_smem) {
   const size_t nb = (size_t)1 << (level + k);
   size_t b = (((nb + 1) * ((size_t)1 << copies_log2) * 12 + 15) / 16) * 16;
-  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4);
+  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
   return b;
 }
 
 template <int WIN, bool ROOT>
-void launch_sweep(bool smem, bool tsm, int grid, size_t bytes, cudaStream_t st, const SweepArgs &a) {
-  if (smem && tsm) sweep_kernel<WIN, true, ROOT, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else if (smem) sweep_kernel<WIN, true, ROOT, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else if (tsm) sweep_kernel<WIN, false, ROOT, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else sweep_kernel<WIN, false, ROOT, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+void launch_sweep(bool smem, bool tsm, bool idx16, int grid, size_t bytes, cudaStream_t st,
+                  const SweepArgs &a) {
+  if (smem && idx16) sweep_kernel<WIN, true, ROOT, true, uint16_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else if (smem) sweep_kernel<WIN, true, ROOT, true, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else if (tsm) sweep_kernel<WIN, false, ROOT, true, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else sweep_kernel<WIN, false, ROOT, false, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
 }
 
-void launch_sweep_any(int win, bool root, bool smem, bool tsm, int grid, size_t bytes, cudaStream_t st,
-                      const SweepArgs &a) {
+void launch_sweep_any(int win, bool root, bool smem, bool tsm, bool idx16, int grid, size_t bytes,
+                      cudaStream_t st, const SweepArgs &a) {
   if (root) {
     switch (win) {
-      case WIN_I32: launch_sweep<WIN_I32, true>(smem, tsm, grid, bytes, st, a); break;
-      case WIN_I64: launch_sweep<WIN_I64, true>(smem, tsm, grid, bytes, st, a); break;
-      case WIN_F64: launch_sweep<WIN_F64, true>(smem, tsm, grid, bytes, st, a); break;
-      default: launch_sweep<WIN_CONST, true>(smem, tsm, grid, bytes, st, a); break;
+      case WIN_I32: launch_sweep<WIN_I32, true>(smem, tsm, idx16, grid, bytes, st, a); break;
+      case WIN_I64: launch_sweep<WIN_I64, true>(smem, tsm, idx16, grid, bytes, st, a); break;
+      case WIN_F64: launch_sweep<WIN_F64, true>(smem, tsm, idx16, grid, bytes, st, a); break;
+      default: launch_sweep<WIN_CONST, true>(smem, tsm, idx16, grid, bytes, st, a); break;
     }
   } else {
     switch (win) {
-      case WIN_I32: launch_sweep<WIN_I32, false>(smem, tsm, grid, bytes, st, a); break;
-      case WIN_I64: launch_sweep<WIN_I64, false>(smem, tsm, grid, bytes, st, a); break;
-      default: launch_sweep<WIN_CONST, false>(smem, tsm, grid, bytes, st, a); break;
+      case WIN_I32: launch_sweep<WIN_I32, false>(smem, tsm, idx16, grid, bytes, st, a); break;
+      case WIN_I64: launch_sweep<WIN_I64, false>(smem, tsm, idx16, grid, bytes, st, a); break;
+      default: launch_sweep<WIN_CONST, false>(smem, tsm, idx16, grid, bytes, st, a); break;
     }
   }
+}
+
+template <int WIN>
+void launch_refine(bool idx16, int grid, size_t bytes, cudaStream_t st, const RefineArgs &a) {
+  if (idx16) sweep_refine_kernel<WIN, uint16_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else sweep_refine_kernel<WIN, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
 }
 
 void prepare_funcs(coupe_b200_ctx *c) {
   if (c->funcs_ready) return;
   const int m = (int)c->max_smem;
 #define SETATTR(fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, m))
-#define SETBOTH(win, root)                            \
-  SETATTR((sweep_kernel<win, true, root, true>));     \
-  SETATTR((sweep_kernel<win, true, root, false>));    \
-  SETATTR((sweep_kernel<win, false, root, true>));    \
-  SETATTR((sweep_kernel<win, false, root, false>))
-  SETBOTH(WIN_I32, true);
-  SETBOTH(WIN_I64, true);
-  SETBOTH(WIN_F64, true);
-  SETBOTH(WIN_CONST, true);
-  SETBOTH(WIN_I32, false);
-  SETBOTH(WIN_I64, false);
-  SETBOTH(WIN_CONST, false);
-  SETATTR((sweep_refine_kernel<WIN_I32>));
-  SETATTR((sweep_refine_kernel<WIN_I64>));
-  SETATTR((sweep_refine_kernel<WIN_CONST>));
-#undef SETBOTH
+#define SETALL(win, root)                                           \
+  SETATTR((sweep_kernel<win, true, root, true, uint16_t>));         \
+  SETATTR((sweep_kernel<win, true, root, true, uint32_t>));         \
+  SETATTR((sweep_kernel<win, false, root, true, uint32_t>));        \
+  SETATTR((sweep_kernel<win, false, root, false, uint32_t>))
+  SETALL(WIN_I32, true);
+  SETALL(WIN_I64, true);
+  SETALL(WIN_F64, true);
+  SETALL(WIN_CONST, true);
+  SETALL(WIN_I32, false);
+  SETALL(WIN_I64, false);
+  SETALL(WIN_CONST, false);
+  SETATTR((sweep_refine_kernel<WIN_I32, uint16_t>));
+  SETATTR((sweep_refine_kernel<WIN_I64, uint16_t>));
+  SETATTR((sweep_refine_kernel<WIN_CONST, uint16_t>));
+  SETATTR((sweep_refine_kernel<WIN_I32, uint32_t>));
+  SETATTR((sweep_refine_kernel<WIN_I64, uint32_t>));
+  SETATTR((sweep_refine_kernel<WIN_CONST, uint32_t>));
+#undef SETALL
 #undef SETATTR
   c->funcs_ready = true;
 }
@@ -283,16 +293,12 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
   if (p.smem) {
     p.copies_log2 = std::min(5, c->nb_smem_log2 - (level + p.k));
     p.bytes = sweep_smem_bytes(level, p.k, p.copies_log2, true);
-    if (p.bytes > c->max_smem) {
-      p.table_in_smem = false;
-      p.bytes = sweep_smem_bytes(level, p.k, p.copies_log2, false);
-    }
     if (p.bytes > c->max_smem) p.smem = false;
   }
   if (!p.smem) {
     p.k = std::max(1, std::min(c->kmax_a, 17 - level));
     p.copies_log2 = 0;
-    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * sizeof(float4);
+    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
     p.table_in_smem = tb <= 64 * 1024;
     p.bytes = p.table_in_smem ? tb : 0;
   }
@@ -354,6 +360,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->tsp_a.ensure(max_nodes * sizeof(float));
   c->tsp_b.ensure(max_nodes * sizeof(float));
   c->target.ensure(max_nodes * sizeof(uint32_t));
+  c->node_rt.ensure(max_nodes * sizeof(uint2));
+  c->rfast.ensure(max_nodes * sizeof(float2));
   const bool narrow_w = w_dev && (wtype == WT_F64 || (wtype == WT_I64 && L > 1));
   if (narrow_w) c->w32.ensure(npad * sizeof(int));
   c->gp.ensure(sizeof(GlobalParams));
@@ -373,7 +381,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   }
   GlobalParams *gp = c->gp.as<GlobalParams>();
   float *x[3] = {c->xcols.as<float>(), c->xcols.as<float>() + npad, c->xcols.as<float>() + 2 * npad};
-  uint32_t *ids = c->ids.as<uint32_t>();
+  void *ids = c->ids.p;
 
   // ---- global point count ---------------------------------------------------
   unsigned long long n_global = n;
@@ -478,8 +486,6 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   const size_t ngroups = (n + 3) / 4;
   const int sweep_grid =
       std::max(1, (int)std::min<size_t>((size_t)c->num_sms, (ngroups + SWEEP_THREADS - 1) / SWEEP_THREADS));
-  const int refine_grid =
-      std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
   unsigned long long *hist_w = c->hist_w.as<unsigned long long>();
   uint32_t *hist_min = c->hist_min.as<uint32_t>();
   int *w32 = narrow_w ? c->w32.as<int>() : nullptr;
@@ -510,18 +516,37 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     CU(cudaEventRecord(c->events[ev_used + 1], st));
     ev_used += 2;
   };
+  uint2 *node_rt = c->node_rt.as<uint2>();
+  // every level in shared-memory mode keeps (node << k) + bin below 2^16
+  bool idx16 = true;
+  for (int level = 0; level < L; ++level) {
+    const FirstPlan pl = plan_first(c, level);
+    idx16 = idx16 && pl.smem && level + pl.k <= 16;
+  }
+  float2 *rfast = c->rfast.as<float2>();
+  // histogram slots a refinement pass may use at a level (shared memory next to the match queue
+  // and, when it fits, the per-node target table)
+  auto refine_cap = [&](int level, bool &rts, size_t &rt_bytes) {
+    rt_bytes = ((size_t)1 << level) * sizeof(uint32_t);
+    rts = rt_bytes <= 64 * 1024;
+    const size_t fixed = (size_t)REFINE_QBYTES + (rts ? rt_bytes : 0) + 64;
+    return (uint32_t)std::min<size_t>((size_t)1 << c->nb_smem_log2, (c->max_smem - fixed) / 12);
+  };
   uint32_t w_wide = 0;
-  auto run_walk = [&](int level, int k, int k0, int first) {
-    CU(cudaMemsetAsync(&gp->unresolved, 0, 4, st));
-    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, rtable, tr,
-                tolerance, level, k, D, first, level == L - 1, w_is_const, k0,
+  auto run_walk = [&](int level, int k, int k0, int first, uint32_t rank_limit) {
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
+                tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit,
                 plan_first(c, level + 1).k};
     const size_t bytes = ((size_t)2 << k) * 12;
-    const int nodes = 1 << level;
+    const uint32_t nodes = 1u << level;
     if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     else if (wtype == WT_I64) walk_kernel<WT_I64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
-    R.launched();
+    bool rts_;
+    size_t rtb_;
+    rank_unresolved_kernel<<<1, 1024, 0, st>>>(target, nodes, node_rt, rtable, rfast,
+                                               refine_cap(level, rts_, rtb_), c->kmax_refine, gp);
+    R.launched(2);
     CU(cudaMemcpyAsync(c->h_pinned, &gp->unresolved, 8, cudaMemcpyDeviceToHost, st));
     R.sync();
     w_wide = c->h_pinned[1];
@@ -555,14 +580,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.k = k;
     sa.kprev = kprev;
     sa.copies_log2 = plan.copies_log2;
-    sa.table_in_smem = plan.table_in_smem;
     sa.w_vec = ((uintptr_t)wp % 16) == 0;
     if (!smem) {
       fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb);
       R.launched();
     }
     time_begin(0);
-    launch_sweep_any(win, level == 0, smem, plan.table_in_smem, sweep_grid, plan.bytes, st, sa);
+    launch_sweep_any(win, level == 0, smem, plan.table_in_smem, idx16, sweep_grid, plan.bytes, st, sa);
     time_end();
     R.launched();
     S.dense_sweeps += 1;
@@ -573,7 +597,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     }
     R.allreduce(hist_w, nb, ncclUint64, ncclSum);
     R.allreduce(hist_min, nb, ncclUint32, ncclMin);
-    uint32_t unresolved = run_walk(level, k, k, 1);
+    uint32_t unresolved = run_walk(level, k, k, 1, 0);
     if (level == 0 && w32) {  // from here on the sweeps read the narrowed weights
       if (c->world > 1 && wtype == WT_I64) {  // every rank must take the same path
         R.allreduce(&gp->w_wide, 1, ncclUint32, ncclMax);
@@ -590,26 +614,32 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     // ---- sparse refinement passes while some bisection is undecided ----------
     int guard = 0;
     while (unresolved > 0) {
-      if (++guard > 400) return COUPE_ERR_CRASH;  // cannot happen: f32 brackets shrink
-      const int kr = std::max(1, std::min(c->kmax_refine, 17 - level));
-      const uint32_t nbr = 1u << (level + kr);
-      fill_hist_kernel<<<(nbr + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nbr);
-      R.launched();
-      const size_t tbytes = ((size_t)1 << level) * sizeof(uint32_t);
-      const int tsm = tbytes <= 96 * 1024;
-      RefineArgs ra{n, x[axis], ids, wp, gp, target, rtable, hist_w, hist_min, level, kr, k, tsm};
+      if (++guard > 100000) return COUPE_ERR_CRASH;  // cannot happen: f32 brackets shrink
+      // ranked histograms of as many undecided nodes as shared memory holds, 2^kr bins each
+      bool rts;
+      size_t rt_bytes;
+      const uint32_t cap = refine_cap(level, rts, rt_bytes);
+      const int kr = refine_bits(unresolved, cap, c->kmax_refine);
+      const uint32_t limit = std::min<uint32_t>(unresolved, cap >> kr);
+      const uint32_t nslots = limit << kr;
+      const size_t rbytes =
+          (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
+      RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
+                    c->part_min.as<uint32_t>(), nslots, limit, level, kr, k, rts};
       time_begin(1);
       switch (win) {
-        case WIN_I32: sweep_refine_kernel<WIN_I32><<<refine_grid, 512, tsm ? tbytes : 0, st>>>(ra); break;
-        case WIN_I64: sweep_refine_kernel<WIN_I64><<<refine_grid, 512, tsm ? tbytes : 0, st>>>(ra); break;
-        default: sweep_refine_kernel<WIN_CONST><<<refine_grid, 512, tsm ? tbytes : 0, st>>>(ra); break;
+        case WIN_I32: launch_refine<WIN_I32>(idx16, sweep_grid, rbytes, st, ra); break;
+        case WIN_I64: launch_refine<WIN_I64>(idx16, sweep_grid, rbytes, st, ra); break;
+        default: launch_refine<WIN_CONST>(idx16, sweep_grid, rbytes, st, ra); break;
       }
       time_end();
-      R.launched();
+      reduce_partials_kernel<<<(nslots + 31) / 32, 256, 0, st>>>(ra.part_w, ra.part_min, sweep_grid,
+                                                                 nslots, hist_w, hist_min);
+      R.launched(2);
       S.refine_sweeps += 1;
-      R.allreduce(hist_w, nbr, ncclUint64, ncclSum);
-      R.allreduce(hist_min, nbr, ncclUint32, ncclMin);
-      unresolved = run_walk(level, kr, k, 0);
+      R.allreduce(hist_w, nslots, ncclUint64, ncclSum);
+      R.allreduce(hist_min, nslots, ncclUint32, ncclMin);
+      unresolved = run_walk(level, kr, k, 0, limit);
     }
     std::swap(cur, nxt);
     std::swap(tab_cur, tab_next);
@@ -621,9 +651,12 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   // ---- final ids -------------------------------------------------------------
   {
     const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
-    emit_kernel<<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, kprev, gp,
-                                      reinterpret_cast<unsigned long long *>(part_dev),
-                                      ((uintptr_t)part_dev % 16) == 0);
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(part_dev);
+    const int out_vec = ((uintptr_t)part_dev % 16) == 0;
+    if (idx16)
+      emit_kernel<uint16_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, kprev, gp, out, out_vec);
+    else
+      emit_kernel<uint32_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, kprev, gp, out, out_vec);
     R.launched();
   }
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
@@ -696,7 +729,7 @@ void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->tsp_a, &c->tsp_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
+  for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->node_rt, &c->rfast, &c->tsp_a, &c->tsp_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
                  &c->nodes_b, &c->table_a, &c->table_b, &c->thi_a, &c->thi_b, &c->rtable, &c->gp, &c->tr_visited,
                  &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
     b->release();

@@ -328,7 +328,7 @@ struct SweepArgs {
   size_t n;
   const float *x;            // coordinate on this level's axis
   const float *xp;           // coordinate on the previous level's axis (refined parents only)
-  uint32_t *idx;             // in: idx of the previous level (level >= 1); out: idx of this level
+  void *idx;                 // in: idx of the previous level (level >= 1); out: idx of this level
   const void *w;             // weights in the kernel's WIN format (null for WIN_CONST)
   int *w32_out;              // root level: narrowed i32 copy of i64 / f64 weights, or null
   GlobalParams *gp;
@@ -341,7 +341,6 @@ struct SweepArgs {
   uint32_t *hist_min;
   int level, k, kprev;
   int copies_log2;           // SMEM mode: 2^copies_log2 lane-private copies per block
-  int table_in_smem;
   int w_vec;                 // weights are 16-byte aligned
 };
 
@@ -361,17 +360,6 @@ __device__ __noinline__ uint32_t descend_exact(float x, float lo, float hi, int 
   return bin;
 }
 
-// Bin of x: one multiply + floor when x is provably away from every bin
-// boundary (fast_bin_params), the exact descend otherwise.
-__device__ __forceinline__ uint32_t bin_of(float x, float lo, float inv, float half_m_eps,
-                                           const float *hi_ptr, int k) {
-  const float t = __fmul_rn(__fsub_rn(x, lo), inv);
-  const float fl = floorf(t);
-  const float fr = __fsub_rn(t, fl);
-  if (fabsf(fr - 0.5f) < half_m_eps) return (uint32_t)(int)fl;
-  return descend_exact(x, lo, __ldg(hi_ptr), k);
-}
-
 // Child (0 = left, 1 = right) of a point whose previous-level bin is b.
 __device__ __forceinline__ uint32_t child_of(uint32_t b, uint32_t sbword, const float *xp, size_t i,
                                              const float *split_ptr) {
@@ -381,22 +369,69 @@ __device__ __forceinline__ uint32_t child_of(uint32_t b, uint32_t sbword, const 
   return child;
 }
 
-template <bool SMEM>
-__device__ __forceinline__ void accumulate(uint32_t slot, long long w, uint32_t key, uint32_t *s_lo,
-                                           int32_t *s_hi, uint32_t *s_min,
-                                           unsigned long long *hist_w, uint32_t *hist_min) {
-  if (SMEM) {
+// The slot of one point with no shortcut: exact child, exact descend.  Taken by
+// the few points that sit within rounding of a bin boundary or in the bin a
+// refined split of the parent fell into.
+__device__ __noinline__ uint32_t slot_exact(const SweepArgs &a, uint32_t pv, float x, size_t i,
+                                            bool root) {
+  const uint32_t p = pv >> a.kprev;
+  const float4 e = __ldg(&a.table[p]);
+  uint32_t node = 0;
+  if (!root)
+    node = 2 * p + child_of(pv & ((1u << a.kprev) - 1), __float_as_uint(e.w), a.xp, i, a.table_split + p);
+  return (node << a.k) + descend_exact(x, e.x, __ldg(a.table_hi + p), a.k);
+}
+
+// --- shared-memory atomics on 32-bit shared addresses -------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// min into [addr] only when it lowers the value seen by a plain load first
+__device__ __forceinline__ void reds_min_if_lower(uint32_t addr, uint32_t key) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+      "ld.shared.u32 c, [%0];\n\t"
+      "setp.lt.u32 p, %1, c;\n\t"
+      "@p red.shared.min.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(key)
+      : "memory");
+}
+
+// One point into the block-private histogram.  lo_addr: shared address of the
+// low sum word of the slot; the high word and the min key sit hi_off / min_off
+// bytes further.
+template <int WIN>
+__device__ __forceinline__ void accumulate_smem(uint32_t lo_addr, uint32_t hi_off, uint32_t min_off,
+                                                long long w, uint32_t key) {
+  if (WIN == WIN_CONST) {
+    reds_add(lo_addr, 1u);  // a block sees fewer than 2^32 points: the count cannot wrap
+  } else {
     // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
     const uint32_t wlo = (uint32_t)w;
-    const uint32_t old = atomicAdd(&s_lo[slot], wlo);
+    const uint32_t old = atoms_add(lo_addr, wlo);
     int hinc = (int)(w >> 32);
     if (old > ~wlo) ++hinc;  // carry out of the low word
-    if (hinc != 0) atomicAdd(&s_hi[slot], hinc);
-    if (key < s_min[slot]) atomicMin(&s_min[slot], key);
-  } else {
-    atomicAdd(&hist_w[slot], (unsigned long long)w);
-    if (key < __ldcg(&hist_min[slot])) atomicMin(&hist_min[slot], key);
+    if (hinc != 0) reds_add(lo_addr + hi_off, (uint32_t)hinc);
   }
+  reds_min_if_lower(lo_addr + min_off, key);
+}
+
+__device__ __forceinline__ void accumulate_global(unsigned long long *hist_w, uint32_t *hist_min,
+                                                  uint32_t slot, long long w, uint32_t key) {
+  atomicAdd(&hist_w[slot], (unsigned long long)w);
+  if (key < __ldcg(&hist_min[slot])) atomicMin(&hist_min[slot], key);
 }
 
 // Raw (unconverted) weight words of four consecutive points, so that the loads
@@ -456,32 +491,63 @@ struct RawW4<WIN_F64> {
   }
 };
 
-template <int WIN, bool ROOT>
+// idx words of four consecutive points: 16-bit when every level of the call
+// keeps (node, bin) below 2^16, 32-bit otherwise.
+template <class IDX>
+struct Idx4;
+template <>
+struct Idx4<uint32_t> {
+  uint4 v;
+  __device__ __forceinline__ void load(const void *p, size_t i0) {
+    v = __ldcs(reinterpret_cast<const uint4 *>(static_cast<const uint32_t *>(p) + i0));
+  }
+  __device__ __forceinline__ void get(uint32_t (&o)[4]) const { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  __device__ static __forceinline__ void store(void *p, size_t i0, const uint32_t (&s)[4]) {
+    __stcs(reinterpret_cast<uint4 *>(static_cast<uint32_t *>(p) + i0), make_uint4(s[0], s[1], s[2], s[3]));
+  }
+};
+template <>
+struct Idx4<uint16_t> {
+  uint2 v;
+  __device__ __forceinline__ void load(const void *p, size_t i0) {
+    v = __ldcs(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(p) + i0));
+  }
+  __device__ __forceinline__ void get(uint32_t (&o)[4]) const {
+    o[0] = v.x & 0xFFFFu; o[1] = v.x >> 16; o[2] = v.y & 0xFFFFu; o[3] = v.y >> 16;
+  }
+  __device__ static __forceinline__ void store(void *p, size_t i0, const uint32_t (&s)[4]) {
+    __stcs(reinterpret_cast<uint2 *>(static_cast<uint16_t *>(p) + i0),
+           make_uint2(s[0] | (s[1] << 16), s[2] | (s[3] << 16)));
+  }
+};
+
+template <int WIN, bool ROOT, class IDX>
 struct Group4 {  // everything the sweep reads for four consecutive points
-  uint4 pv;
+  Idx4<IDX> pv;
   float4 x;
   RawW4<WIN> w;
   __device__ __forceinline__ void load(const SweepArgs &a, size_t i0, bool vec) {
-    if (!ROOT) pv = __ldcs(reinterpret_cast<const uint4 *>(a.idx + i0));
-    else pv = make_uint4(0, 0, 0, 0);
+    if (!ROOT) pv.load(a.idx, i0);
     x = __ldcs(reinterpret_cast<const float4 *>(a.x + i0));
     w.load(a.w, i0, vec);
   }
 };
 
-template <int WIN, bool SMEM, bool ROOT, bool TSM>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const SweepArgs a) {
+// TSM: the per-parent table is staged in shared memory (always in SMEM mode).
+template <int WIN, bool SMEM, bool ROOT, bool TSM, class IDX>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = a.k, level = a.level, kprev = a.kprev;
   const uint32_t nb = 1u << (level + k);  // bins of this level
   const int ncopy = 1 << a.copies_log2;
   const uint32_t cstride = nb + 1;        // copies are skewed by one bank
-  const size_t nacc = SMEM ? (size_t)cstride * ncopy : 0;
+  const uint32_t nacc = SMEM ? cstride * (uint32_t)ncopy : 0;
   uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
-  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + nacc);
-  uint32_t *s_min = reinterpret_cast<uint32_t *>(s_hi + nacc);
-  float4 *s_table = reinterpret_cast<float4 *>(smem_raw + ((nacc * 12 + 15) / 16) * 16);
+  uint32_t *s_hi = s_lo + nacc;
+  uint32_t *s_min = s_hi + nacc;
+  float4 *s_table = reinterpret_cast<float4 *>(smem_raw + (((size_t)nacc * 12 + 15) / 16) * 16);
   const int nparents = 1 << (level > 0 ? level - 1 : 0);
+  float *s_split = reinterpret_cast<float *>(s_table + (TSM ? nparents : 0));
   if (SMEM) {
     const uint32_t total = cstride * (uint32_t)ncopy;
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
@@ -491,13 +557,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const SweepArgs
     }
   }
   if (TSM)
-    for (int i = threadIdx.x; i < nparents; i += blockDim.x) s_table[i] = a.table[i];
+    for (int i = threadIdx.x; i < nparents; i += blockDim.x) {
+      s_table[i] = a.table[i];
+      s_split[i] = a.table_split[i];
+    }
   __syncthreads();
   const double scale = (WIN == WIN_F64) ? a.gp->scale : 1.0;
-  const uint32_t copy_off = SMEM ? (threadIdx.x & (ncopy - 1)) * cstride : 0;
-  uint32_t *c_lo = s_lo + copy_off;
-  int32_t *c_hi = s_hi + copy_off;
-  uint32_t *c_min = s_min + copy_off;
+  const uint32_t lo_base = smem_addr(s_lo) + (SMEM ? (threadIdx.x & (ncopy - 1)) * cstride * 4 : 0);
+  const uint32_t hi_off = nacc * 4, min_off = nacc * 8;
   const uint32_t bmask = (1u << kprev) - 1;
   const bool vec = a.w_vec != 0;
   const bool narrow = ROOT && (WIN == WIN_I64 || WIN == WIN_F64) && a.w32_out != nullptr;
@@ -507,27 +574,46 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const SweepArgs
   const size_t nfull = n / 4;  // groups of four points without bounds checks
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Group4<WIN, ROOT> cur, nxt;
+  Group4<WIN, ROOT, IDX> cur, nxt;
   if (g < nfull) cur.load(a, g * 4, vec);
   while (g < nfull) {
     const size_t gn = g + stride;
     if (gn < nfull) nxt.load(a, gn * 4, vec);  // in flight while this group is processed
     const size_t i0 = g * 4;
-    const uint32_t pv[4] = {cur.pv.x, cur.pv.y, cur.pv.z, cur.pv.w};
+    uint32_t pv[4] = {0, 0, 0, 0};
+    if (!ROOT) cur.pv.get(pv);
     const float x[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
     long long w[4];
     cur.w.get(scale, w);
     uint32_t slot[4];
+    uint32_t slow = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t p = pv[j] >> kprev;
       const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
       uint32_t node = 0;
-      if (!ROOT)
-        node = 2 * p + child_of(pv[j] & bmask, __float_as_uint(e.w), a.xp, i0 + j, a.table_split + p);
-      slot[j] = (node << k) + bin_of(x[j], e.x, e.y, e.z, a.table_hi + p, k);
+      if (!ROOT) {  // child = (bin >= split bin) unless the parent's split was refined inside this bin
+        const uint32_t sbword = __float_as_uint(e.w);
+        const int d = (int)(pv[j] & bmask) - (int)(sbword & 0xFFFFu);
+        bool right = d >= 0;
+        if (d == 0 && (sbword & SB_REFINED))  // the bin the parent's refined split fell into
+          right = !(__ldg(a.xp + i0 + j) < (TSM ? s_split[p] : __ldg(a.table_split + p)));
+        node = 2 * p + (right ? 1u : 0u);
+      }
+      // bin = floor((x - lo) * 2^k / width), trusted when x is provably away from every
+      // bin boundary (fast_bin_params); floor by adding 2^23 rounding down
+      const float t = __fmul_rn(__fsub_rn(x[j], e.x), e.y);
+      const float tf = __fadd_rd(t, 8388608.f);
+      const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
+      if (!(fabsf(fr - 0.5f) < e.z)) slow |= 1u << j;
+      slot[j] = (node << k) + (__float_as_uint(tf) & 0x7FFFFFu);
     }
-    __stcs(reinterpret_cast<uint4 *>(a.idx + i0), make_uint4(slot[0], slot[1], slot[2], slot[3]));
+    if (slow) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (slow & (1u << j)) slot[j] = slot_exact(a, pv[j], x[j], i0 + j, ROOT);
+    }
+    Idx4<IDX>::store(a.idx, i0, slot);
     if (narrow) {
       __stcs(reinterpret_cast<int4 *>(a.w32_out + i0),
              make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
@@ -535,28 +621,27 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const SweepArgs
         wide = wide || w[0] != (int)w[0] || w[1] != (int)w[1] || w[2] != (int)w[2] || w[3] != (int)w[3];
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      accumulate<SMEM>(slot[j], w[j], f2key(x[j]), c_lo, c_hi, c_min, a.hist_w, a.hist_min);
+    for (int j = 0; j < 4; ++j) {
+      if (SMEM) accumulate_smem<WIN>(lo_base + slot[j] * 4, hi_off, min_off, w[j], f2key(x[j]));
+      else accumulate_global(a.hist_w, a.hist_min, slot[j], w[j], f2key(x[j]));
+    }
     cur = nxt;
     g = gn;
   }
   // tail: the last n % 4 points, one thread
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
     for (size_t i = nfull * 4; i < n; ++i) {
-      const uint32_t pv = ROOT ? 0u : a.idx[i];
-      const uint32_t p = pv >> kprev;
-      const float4 e = a.table[p];
-      uint32_t node = 0;
-      if (!ROOT) node = 2 * p + child_of(pv & bmask, __float_as_uint(e.w), a.xp, i, a.table_split + p);
+      const uint32_t pv = ROOT ? 0u : static_cast<const IDX *>(a.idx)[i];
       const float x = a.x[i];
-      const uint32_t slot = (node << k) + descend_exact(x, e.x, a.table_hi[p], k);
-      a.idx[i] = slot;
+      const uint32_t slot = slot_exact(a, pv, x, i, ROOT);
+      static_cast<IDX *>(a.idx)[i] = (IDX)slot;
       const long long w = load_w1<WIN>(a.w, i, scale);
       if (narrow) {
         a.w32_out[i] = (int)w;
         if (WIN == WIN_I64) wide = wide || w != (int)w;
       }
-      accumulate<SMEM>(slot, w, f2key(x), c_lo, c_hi, c_min, a.hist_w, a.hist_min);
+      if (SMEM) accumulate_smem<WIN>(lo_base + slot * 4, hi_off, min_off, w, f2key(x));
+      else accumulate_global(a.hist_w, a.hist_min, slot, w, f2key(x));
     }
   }
   if (ROOT && WIN == WIN_I64 && wide) a.gp->w_wide = 1;
@@ -569,7 +654,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const SweepArgs
       uint32_t m = KEY_EMPTY;
       for (int c = 0; c < ncopy; ++c) {
         const uint32_t s = c * cstride + i;
-        acc += ((unsigned long long)(uint32_t)s_hi[s] << 32) + s_lo[s];
+        acc += ((unsigned long long)s_hi[s] << 32) + s_lo[s];
         m = min(m, s_min[s]);
       }
       pw[i] = (long long)acc;
@@ -620,59 +705,196 @@ fill_hist_kernel(unsigned long long *hist_w, uint32_t *hist_min, uint32_t nb) {
 
 // ---------------------------------------------------------------------------
 // Sparse sweep: only the points of the one first-pass bin an undecided
-// bisection narrowed down to contribute; every other point costs its 4-byte
-// idx word and nothing else.
+// bisection narrowed down to contribute; every other point costs its idx word
+// and nothing else.  The undecided nodes are ranked (rank_unresolved_kernel) so
+// that their histograms are dense: slot = (rank << k) + bin, kept in shared
+// memory like the dense pass.
 // ---------------------------------------------------------------------------
 struct RefineArgs {
   size_t n;
   const float *x;
-  const uint32_t *idx;     // idx of this level
+  const void *idx;         // idx of this level
   const void *w;
-  const GlobalParams *gp;
-  const uint32_t *target;  // per node: idx value of the bin under refinement, TARGET_NONE if resolved
+  const uint2 *node_rt;    // per node: {idx value of the bin under refinement, rank}; TARGET_NONE if resolved
   const float4 *rtable;    // per node: {lo, hi, hi inclusive, -}
-  unsigned long long *hist_w;
-  uint32_t *hist_min;
+  const float2 *rfast;     // per node: {2^k / width, 0.5 - eps} of the refinement bracket
+  long long *part_w;       // per-block partial histograms [grid][nslots]
+  uint32_t *part_min;
+  uint32_t nslots;         // refined nodes << k
+  uint32_t rank_limit;     // nodes ranked at or above wait for a later pass
   int level, k, k0;        // k0: bins of the dense pass (idx = (node << k0) + bin)
-  int target_in_smem;
+  int rt_in_smem;
 };
 
-template <int WIN>
-__global__ void __launch_bounds__(512) sweep_refine_kernel(const RefineArgs a) {
+constexpr int REFINE_BATCH = 64;                   // matches a warp lets build up before it drains them
+constexpr int REFINE_QCAP = REFINE_BATCH + 4 * 32;  // + what one warp iteration can add
+constexpr int REFINE_QBYTES = (SWEEP_THREADS / 32) * REFINE_QCAP * 8;
+
+// Per warp, two phases: (1) every lane tests its four idx words against the
+// per-node targets and appends the matches to the warp's queue in shared
+// memory (a warp scan assigns the places, no atomics, no block barrier);
+// (2) once a batch has built up the warp drains it with every lane busy.
+// Matches are a few percent of the points, so without the queue nearly every
+// warp would run the expensive branch for one or two lanes at a time.
+template <int WIN, class IDX>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *s_target = reinterpret_cast<uint32_t *>(smem_raw);
+  const uint32_t nslots = a.nslots;
+  uint32_t *q_all = reinterpret_cast<uint32_t *>(smem_raw);           // [warps][REFINE_QCAP][2]
+  uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw + REFINE_QBYTES);
+  uint32_t *s_hi = s_lo + nslots;
+  uint32_t *s_min = s_hi + nslots;
+  uint32_t *s_tg = s_min + nslots;  // [nodes] target idx of the nodes refined in this pass (rt_in_smem)
   const int k = a.k, k0 = a.k0;
   const uint32_t nodes = 1u << a.level;
-  const bool tsm = a.target_in_smem != 0;
-  if (tsm) {
-    for (uint32_t i = threadIdx.x; i < nodes; i += blockDim.x) s_target[i] = a.target[i];
-    __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+    s_lo[i] = 0;
+    s_hi[i] = 0;
+    s_min[i] = KEY_EMPTY;
   }
+  const bool rts = a.rt_in_smem != 0;
+  if (rts)
+    for (uint32_t i = threadIdx.x; i < nodes; i += blockDim.x) {
+      const uint2 rt = a.node_rt[i];
+      s_tg[i] = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
+    }
+  __syncthreads();
+  const uint32_t lo_base = smem_addr(s_lo);
+  const uint32_t hi_off = nslots * 4, min_off = nslots * 8;
   const size_t n = a.n;
   const size_t ngroups = (n + 3) / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-    const size_t i0 = g * 4;
-    const uint4 vv = __ldcs(reinterpret_cast<const uint4 *>(a.idx + i0));
-    const uint32_t v[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t p = v[j] >> k0;
-      if (p >= nodes) continue;  // padding past n
-      if (v[j] != (tsm ? s_target[p] : __ldg(&a.target[p]))) continue;
-      const size_t i = i0 + j;
+  const size_t g_first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  uint2 *q = reinterpret_cast<uint2 *>(q_all) + (threadIdx.x >> 5) * REFINE_QCAP;  // {iteration*4 + j of lane.., node}
+  uint32_t cnt = 0;  // warp-uniform
+
+  auto drain = [&]() {
+    for (uint32_t e = lane; e < cnt; e += 32) {
+      const uint2 en = q[e];  // x: (iteration << 7) | (lane << 2) | j, y: node
+      const size_t i = (g_first - lane + (size_t)(en.x >> 7) * stride + ((en.x >> 2) & 31)) * 4 + (en.x & 3);
       if (i >= n) continue;
+      const uint32_t p = en.y;
       const float x = __ldg(a.x + i);
-      const float4 e = __ldg(&a.rtable[p]);
-      const bool in = !(x < e.x) && (x < e.y || (e.z != 0.f && x <= e.y));
+      const float4 r = __ldg(&a.rtable[p]);
+      const bool in = !(x < r.x) && (x < r.y || (r.z != 0.f && x <= r.y));
       if (!in) continue;
-      const uint32_t bin = descend_exact(x, e.x, e.y, k);
-      const long long w = load_w1<WIN>(a.w, i, 1.0);
-      const uint32_t slot = (p << k) + bin;
-      atomicAdd(&a.hist_w[slot], (unsigned long long)w);
-      const uint32_t key = f2key(x);
-      if (key < __ldcg(&a.hist_min[slot])) atomicMin(&a.hist_min[slot], key);
+      const uint32_t rank = __ldg(&a.node_rt[p]).y;
+      const float2 f = __ldg(&a.rfast[p]);
+      const float t = __fmul_rn(__fsub_rn(x, r.x), f.x);
+      const float tf = __fadd_rd(t, 8388608.f);
+      const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
+      uint32_t bin = __float_as_uint(tf) & 0x7FFFFFu;
+      if (!(fabsf(fr - 0.5f) < f.y)) bin = descend_exact(x, r.x, r.y, k);
+      accumulate_smem<WIN>(lo_base + ((rank << k) + bin) * 4, hi_off, min_off, load_w1<WIN>(a.w, i, 1.0),
+                           f2key(x));
     }
+    __syncwarp();
+    cnt = 0;
+  };
+
+  Idx4<IDX> cur, nxt;
+  if (g_first < ngroups) cur.load(a.idx, g_first * 4);
+  // every lane of a warp runs the same number of iterations (the warp's first lane decides)
+  const size_t g_warp = g_first - lane;
+  uint32_t it = 0;
+  for (size_t gw = g_warp; gw < ngroups; gw += stride, ++it) {
+    const size_t g = gw + lane;
+    if (g + stride < ngroups) nxt.load(a.idx, (g + stride) * 4);
+    uint32_t mm = 0;  // which of the four points match
+    uint32_t pn[4] = {0, 0, 0, 0};
+    if (g < ngroups) {
+      uint32_t v[4];
+      cur.get(v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pn[j] = (v[j] >> k0) & (nodes - 1);  // masked: the padding past n holds anything
+        uint32_t tg;
+        if (rts) tg = s_tg[pn[j]];
+        else {
+          const uint2 rt = __ldg(&a.node_rt[pn[j]]);
+          tg = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
+        }
+        if (v[j] == tg) mm |= 1u << j;
+      }
+    }
+    if (__any_sync(0xffffffffu, mm != 0)) {
+      const uint32_t c = __popc(mm);
+      uint32_t incl = c;  // inclusive warp scan of the match counts
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+      }
+      uint32_t e = cnt + incl - c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (mm & (1u << j)) q[e++] = make_uint2((it << 7) | (lane << 2) | j, pn[j]);
+      cnt += __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
+      if (cnt >= REFINE_BATCH) drain();
+    }
+    cur = nxt;
+  }
+  drain();
+  __syncthreads();
+  long long *pw = a.part_w + (size_t)blockIdx.x * nslots;
+  uint32_t *pm = a.part_min + (size_t)blockIdx.x * nslots;
+  for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+    pw[i] = (long long)(((unsigned long long)s_hi[i] << 32) + s_lo[i]);
+    pm[i] = s_min[i];
+  }
+}
+
+// How many bins per node the next refinement pass uses: as many as fit `cap`
+// histogram slots for all `unresolved` nodes, at most 2^kmax.  The host runs the
+// same function on the count it reads back.
+__host__ __device__ inline int refine_bits(uint32_t unresolved, uint32_t cap, int kmax) {
+  int kr = 1;
+  while (kr < kmax && ((unsigned long long)unresolved << (kr + 1)) <= cap) ++kr;
+  return kr;
+}
+
+// Ranks the undecided nodes of a level in node order (identical on every GPU),
+// counts them and prepares their fast binning parameters: node_rt[p] =
+// {target idx, rank}, rfast[p] = {2^kr / width, 0.5 - eps}.
+__global__ void __launch_bounds__(1024)
+rank_unresolved_kernel(const uint32_t *__restrict__ target, uint32_t nodes, uint2 *__restrict__ node_rt,
+                       const float4 *__restrict__ rtable, float2 *__restrict__ rfast, uint32_t cap,
+                       int kmax, GlobalParams *gp) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t b = 0; b < nodes; b += blockDim.x) {
+    const uint32_t p = b + threadIdx.x;
+    const uint32_t tg = p < nodes ? target[p] : TARGET_NONE;
+    const bool un = tg != TARGET_NONE;
+    const uint32_t bal = __ballot_sync(0xffffffffu, un);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = s_base;
+    for (uint32_t wv = 0; wv < warp; ++wv) before += s_warp[wv];
+    if (p < nodes) node_rt[p] = make_uint2(tg, before + __popc(bal & ((1u << lane) - 1)));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = s_base;
+      for (uint32_t wv = 0; wv < (blockDim.x >> 5); ++wv) t += s_warp[wv];
+      s_base = t;
+    }
+    __syncthreads();
+  }
+  const uint32_t unresolved = s_base;
+  if (threadIdx.x == 0) gp->unresolved = unresolved;
+  if (unresolved == 0) return;
+  const int kr = refine_bits(unresolved, cap, kmax);
+  for (uint32_t p = threadIdx.x; p < nodes; p += blockDim.x) {
+    if (target[p] == TARGET_NONE) continue;
+    const float4 r = rtable[p];
+    float inv, hme;
+    fast_bin_params(r.x, r.y, kr, inv, hme);
+    rfast[p] = make_float2(inv, hme);
   }
 }
 
@@ -720,11 +942,13 @@ struct WalkArgs {
   float *table_next_hi;      // per node: hi on the next axis
   float *table_next_split;   // per node: split position on this axis
   uint32_t *target;          // per node: idx value under refinement
+  const uint2 *node_rt;      // per node: {target, rank} of the refinement pass being walked
   float4 *rtable;            // per node: refinement bracket
   Trace trace;
   double tolerance;
   int level, k, D, first, last_level, w_is_const;
   int k0;                    // bins of this level's dense pass
+  uint32_t rank_limit;       // refinement: nodes ranked at or above were not swept this pass
   int k_next;                // bins of the next level's dense pass
 };
 
@@ -740,6 +964,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   const int axis = a.level % a.D, next_axis = (a.level + 1) % a.D;
   const uint32_t heap = ((1u << a.level) - 1) + p;
 
+  if (!a.first && !ns.done && a.node_rt[p].y >= a.rank_limit) return;  // waits for a later pass
   if (a.first ? !ns.alive : ns.done) {
     if (a.first && threadIdx.x == 0) {  // empty node: rcb_recurse returns at once (:586-588)
       ns.done = 1;
@@ -755,9 +980,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     return;
   }
   const unsigned long long wscale = a.w_is_const ? (unsigned long long)a.gp->wconst : 1ull;
+  const size_t hbase = (size_t)(a.first ? p : a.node_rt[p].y) * nb;  // refinement histograms are ranked
   for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-    wtree[nb + i] = a.hist_w[(size_t)p * nb + i] * wscale;
-    mtree[nb + i] = a.hist_min[(size_t)p * nb + i];
+    wtree[nb + i] = a.hist_w[hbase + i] * wscale;
+    mtree[nb + i] = a.hist_min[hbase + i];
   }
   __syncthreads();
   for (int d = k - 1; d >= 0; --d) {
@@ -871,7 +1097,6 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     if (a.first) ns.sb = t - nb;  // the dense-pass bin the bracket has shrunk to
     a.target[p] = (p << a.k0) + ns.sb;
     a.rtable[p] = make_float4(lo, hi, hi_incl ? 1.f : 0.f, 0.f);
-    atomicAdd(&a.gp->unresolved, 1u);
     return;
   }
   ns.done = 1;
@@ -925,8 +1150,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
 // ---------------------------------------------------------------------------
 // Final ids: last child choice, minus the smallest id present (:698-702).
 // ---------------------------------------------------------------------------
+template <class IDX>
 __global__ void __launch_bounds__(512)
-emit_kernel(size_t n, const uint32_t *__restrict__ idx, const float *__restrict__ xp,
+emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp,
             const float4 *__restrict__ table, const float *__restrict__ table_split, int klast,
             const GlobalParams *__restrict__ gp, unsigned long long *__restrict__ out, int out_vec) {
   const uint32_t off = gp->leaf_min;
@@ -935,8 +1161,10 @@ emit_kernel(size_t n, const uint32_t *__restrict__ idx, const float *__restrict_
   const uint32_t bmask = (1u << klast) - 1;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
     const size_t i0 = g * 4;
-    const uint4 vv = __ldcs(reinterpret_cast<const uint4 *>(idx + i0));
-    const uint32_t v[4] = {vv.x, vv.y, vv.z, vv.w};
+    Idx4<IDX> vv;
+    vv.load(idx, i0);
+    uint32_t v[4];
+    vv.get(v);
     unsigned long long r[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
