@@ -119,7 +119,7 @@ def measured_peak():
 def profiled_traffic():
     """Per-launch DRAM bytes of the dense sweep from the committed ncu capture, if any."""
     try:
-        with open(os.path.join(ROOT, "profiles", "sweep_first_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return None
@@ -280,7 +280,7 @@ def run_ours(args):
     achieved = algo_bytes_per_launch * dense_n / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else None
     traffic = profiled_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "sweep_first_kernel<f64 weights, shared-memory histograms>",
+        "bound": "hbm", "kernel": "sweep_kernel (dense sweep of one level: shared-memory histograms, u16 idx, i32 narrowed weights)",
         "achieved": achieved, "peak": peak, "peak_source": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
         "unit": "GB/s", "frac": achieved / peak if achieved else None,
         "algorithmic_bytes_per_launch": algo_bytes_per_launch, "launches_timed": dense_n,

@@ -20,6 +20,7 @@ COUPE_H_SYMBOLS = ["coupe_strerror", "coupe_data_free", "coupe_data_array", "cou
                    "coupe_data_fn", "coupe_rcb", "coupe_rib"]
 COUPE_B200_H_SYMBOLS = ["coupe_b200_ctx_create", "coupe_b200_ctx_destroy", "coupe_b200_nccl_unique_id",
                         "coupe_b200_ctx_init_comm", "coupe_b200_rcb_device", "coupe_b200_rib_device",
+                        "coupe_b200_rcb_host", "coupe_b200_rib_host", "coupe_b200_host_release",
                         "coupe_b200_last_stats", "coupe_b200_last_trace", "coupe_b200_reserve",
                         "coupe_b200_set_option", "coupe_b200_version"]
 
@@ -87,6 +88,12 @@ def lib():
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int,
                       C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]
+    for f in (L.coupe_b200_rcb_host, L.coupe_b200_rib_host):
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                      C.c_void_p, C.c_size_t, C.c_double]
+    L.coupe_b200_host_release.restype = None
+    L.coupe_b200_host_release.argtypes = [C.c_void_p]
     L.coupe_b200_last_stats.restype = C.c_int
     L.coupe_b200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.coupe_b200_last_trace.restype = C.c_int

@@ -63,6 +63,7 @@ class Context:
 
     def close(self):
         if self._h:
+            _lib.lib().coupe_b200_host_release(self._h)
             _lib.lib().coupe_b200_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -164,7 +165,7 @@ def _device_call(rib: bool, ctx: Context | None, part_ids, points, weights, iter
         raise BackendError(err)
 
 
-def _host_call(rib: bool, part_ids, points, weights, iter_count, tolerance):
+def _host_call(rib: bool, ctx, part_ids, points, weights, iter_count, tolerance):
     L = _lib.lib()
     pts = np.ascontiguousarray(points, dtype=np.float64)
     if pts.ndim != 2:
@@ -184,6 +185,14 @@ def _host_call(rib: bool, part_ids, points, weights, iter_count, tolerance):
         raise InputLenMismatch(part_ids.shape[0], wlen)
     if n != part_ids.shape[0]:
         raise InputLenMismatch(part_ids.shape[0], n)
+    if ctx is not None:  # explicit context: the slice-level entry point a language binding uses
+        fn = L.coupe_b200_rib_host if rib else L.coupe_b200_rcb_host
+        err = fn(ctx._h, part_ids.ctypes.data, dim, n, pts.ctypes.data, tag,
+                 None if const else w.ctypes.data, w.ctypes.data if const else None, int(iter_count),
+                 float(tolerance))
+        if err != 0:
+            raise BackendError(err)
+        return
     dp = L.coupe_data_array(n, _lib.COUPE_DOUBLE, pts.ctypes.data)
     dw = (L.coupe_data_constant if const else L.coupe_data_array)(wlen, tag, w.ctypes.data)
     try:
@@ -213,7 +222,7 @@ class Rcb:
         if _is_torch(points):
             _device_call(False, self.context, part_ids, points, weights, self.iter_count, self.tolerance)
         else:
-            _host_call(False, part_ids, points, weights, self.iter_count, self.tolerance)
+            _host_call(False, self.context, part_ids, points, weights, self.iter_count, self.tolerance)
 
 
 @dataclass
@@ -229,4 +238,4 @@ class Rib:
         if _is_torch(points):
             _device_call(True, self.context, part_ids, points, weights, self.iter_count, self.tolerance)
         else:
-            _host_call(True, part_ids, points, weights, self.iter_count, self.tolerance)
+            _host_call(True, self.context, part_ids, points, weights, self.iter_count, self.tolerance)

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -46,7 +47,11 @@ struct DevBuf {
     return true;
   }
 };
-DevBuf g_pts, g_w, g_part;
+// Device staging of the host entry points, one set per context.
+struct Staging {
+  DevBuf pts, w, part;
+};
+std::map<coupe_b200_ctx *, Staging> g_staging;
 
 coupe_b200_ctx *default_ctx() {
   if (g_ctx) return g_ctx;
@@ -91,6 +96,35 @@ bool materialise(const coupe_data *d, size_t elem, std::vector<unsigned char> &o
   return true;
 }
 
+// Host arrays in, host part ids out: copy to the device, run the CUDA path, copy back.
+// Caller holds g_mu.
+int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dimension, uintptr_t n,
+             const double *pts_host, int wtype, const void *w_host, const void *w_const,
+             uintptr_t iter_count, double tolerance) {
+  if (dimension != 2 && dimension != 3) return COUPE_ERR_BAD_DIMENSION;
+  if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
+  if (n == 0) return COUPE_ERR_OK;  // nothing to write (recursive_bisection.rs:685-688)
+  if (!pts_host || !partition || (!w_host && !w_const)) return COUPE_ERR_CRASH;
+  Staging &sg = g_staging[ctx];
+  const size_t pelem = dimension * sizeof(double);
+  const size_t welem = wtype == COUPE_INT ? 4 : 8;
+  if (!sg.pts.ensure(n * pelem) || !sg.part.ensure(n * sizeof(uint64_t))) return COUPE_ERR_ALLOC;
+  if (w_host && !sg.w.ensure(n * welem)) return COUPE_ERR_ALLOC;
+  if (cudaMemcpy(sg.pts.p, pts_host, n * pelem, cudaMemcpyHostToDevice) != cudaSuccess)
+    return COUPE_ERR_CRASH;
+  if (w_host && cudaMemcpy(sg.w.p, w_host, n * welem, cudaMemcpyHostToDevice) != cudaSuccess)
+    return COUPE_ERR_CRASH;
+  auto fn = rib ? coupe_b200_rib_device : coupe_b200_rcb_device;
+  const int err = fn(ctx, nullptr, static_cast<uint64_t *>(sg.part.p), dimension, n,
+                     static_cast<const double *>(sg.pts.p), wtype, w_host ? sg.w.p : nullptr, w_const,
+                     iter_count, tolerance);
+  if (err != COUPE_ERR_OK) return err;
+  static_assert(sizeof(uintptr_t) == sizeof(uint64_t), "usize is 64 bit");
+  if (cudaMemcpy(partition, sg.part.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return COUPE_ERR_CRASH;
+  return COUPE_ERR_OK;
+}
+
 coupe_err run(bool rib, uintptr_t *partition, uintptr_t dimension, const coupe_data *points,
               const coupe_data *weights, uintptr_t iter_count, double tolerance) {
   if (!points || !weights) return COUPE_ERR_CRASH;
@@ -122,22 +156,8 @@ coupe_err run(bool rib, uintptr_t *partition, uintptr_t dimension, const coupe_d
     w_host = w_tmp.data();
   }
 
-  // host -> device, run, device -> host
-  if (!g_pts.ensure(n * pelem) || !g_part.ensure(n * sizeof(uint64_t))) return COUPE_ERR_ALLOC;
-  if (w_host && !g_w.ensure(n * welem)) return COUPE_ERR_ALLOC;
-  if (cudaMemcpy(g_pts.p, pts_host, n * pelem, cudaMemcpyHostToDevice) != cudaSuccess)
-    return COUPE_ERR_CRASH;
-  if (w_host && cudaMemcpy(g_w.p, w_host, n * welem, cudaMemcpyHostToDevice) != cudaSuccess)
-    return COUPE_ERR_CRASH;
-  auto fn = rib ? coupe_b200_rib_device : coupe_b200_rcb_device;
-  const int err = fn(ctx, nullptr, static_cast<uint64_t *>(g_part.p), dimension, n,
-                     static_cast<const double *>(g_pts.p), (int)weights->type,
-                     w_host ? g_w.p : nullptr, w_const, iter_count, tolerance);
-  if (err != COUPE_ERR_OK) return (coupe_err)err;
-  static_assert(sizeof(uintptr_t) == sizeof(uint64_t), "usize is 64 bit");
-  if (cudaMemcpy(partition, g_part.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-    return COUPE_ERR_CRASH;
-  return COUPE_ERR_OK;
+  return (coupe_err)run_host(ctx, rib, partition, dimension, n, static_cast<const double *>(pts_host),
+                             (int)weights->type, w_host, w_const, iter_count, tolerance);
 }
 
 coupe_data *make(coupe_data::Kind kind, uintptr_t len, coupe_type type, const void *ptr,
@@ -185,6 +205,43 @@ coupe_data *coupe_data_constant(uintptr_t len, enum coupe_type type, const void 
 coupe_data *coupe_data_fn(const void *context, uintptr_t len, enum coupe_type type,
                           const void *(*i_th)(const void *, uintptr_t)) {
   return make(coupe_data::FN, len, type, context, i_th);
+}
+
+int coupe_b200_rcb_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+                        const double *points, int wtype, const void *weights, const void *wconst,
+                        uintptr_t iter_count, double tolerance) {
+  if (!ctx) return COUPE_ERR_CRASH;
+  try {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return run_host(ctx, false, partition, dim, n, points, wtype, weights, wconst, iter_count, tolerance);
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;
+  }
+}
+
+int coupe_b200_rib_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+                        const double *points, int wtype, const void *weights, const void *wconst,
+                        uintptr_t iter_count, double tolerance) {
+  if (!ctx) return COUPE_ERR_CRASH;
+  try {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return run_host(ctx, true, partition, dim, n, points, wtype, weights, wconst, iter_count, tolerance);
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;
+  }
+}
+
+void coupe_b200_host_release(coupe_b200_ctx *ctx) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_staging.find(ctx);
+  if (it == g_staging.end()) return;
+  for (DevBuf *b : {&it->second.pts, &it->second.w, &it->second.part})
+    if (b->p) cudaFree(b->p);
+  g_staging.erase(it);
 }
 
 enum coupe_err coupe_rcb(uintptr_t *partition, uintptr_t dimension, const coupe_data *points,

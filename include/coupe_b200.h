@@ -77,6 +77,25 @@ int coupe_b200_rib_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev,
 		uintptr_t n, const double *points_dev, int wtype, const void *weights_dev,
 		const void *wconst_host, uintptr_t iter_count, double tolerance);
 
+/*
+ * The same two algorithms on HOST arrays with an explicit context: copies the
+ * inputs to the device, runs the CUDA path, copies the n part ids back
+ * (`partition` holds n uintptr_t, as in coupe_rcb).  This is what a language
+ * binding that already holds plain slices calls (rust/coupe-gpu: `impl
+ * Partition for GpuRcb`, replacing the body of coupe::Rcb::partition,
+ * recursive_bisection.rs:805-811); coupe_rcb / coupe_rib of coupe.h are these
+ * calls on the process-wide default context after unwrapping the coupe_data
+ * sets.  coupe_b200_host_release frees the device staging buffers a context
+ * accumulated through these calls (call it before coupe_b200_ctx_destroy).
+ */
+int coupe_b200_rcb_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+		const double *points, int wtype, const void *weights, const void *wconst,
+		uintptr_t iter_count, double tolerance);
+int coupe_b200_rib_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+		const double *points, int wtype, const void *weights, const void *wconst,
+		uintptr_t iter_count, double tolerance);
+void coupe_b200_host_release(coupe_b200_ctx *ctx);
+
 /* Counters of the last call. */
 int coupe_b200_last_stats(const coupe_b200_ctx *ctx, coupe_b200_stats *out);
 
