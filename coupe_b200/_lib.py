@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcoupe_b200.so")
+# COUPE_B200_LIB: load another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("COUPE_B200_LIB") or os.path.join(_HERE, "lib", "libcoupe_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 COUPE_ERR = ["OK", "ALLOC", "CRASH", "BAD_DIMENSION", "BAD_TYPE", "BIPART_ONLY", "LEN_MISMATCH",

@@ -666,6 +666,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->events[e], c->events[e + 1]));
     (c->event_kind[e / 2] ? S.refine_sweep_ms : S.dense_sweep_ms) += ms;
+    if (c->time_sweeps > 1) fprintf(stderr, "coupe_b200: %s sweep %zu: %.1f us\n", c->event_kind[e / 2] ? "refine" : "dense", e / 2, ms * 1e3);
   }
   CU(cudaGetLastError());
   return COUPE_ERR_OK;
@@ -825,7 +826,7 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "kmax_refine") c->kmax_refine = (int)std::max<int64_t>(1, std::min<int64_t>(10, value));
   else if (s == "force_global") c->force_global = value != 0;
   else if (s == "trace") c->trace_on = value != 0;
-  else if (s == "time_sweeps") c->time_sweeps = value != 0;
+  else if (s == "time_sweeps") c->time_sweeps = (int)value;
   else return COUPE_ERR_NOT_FOUND;
   return COUPE_ERR_OK;
 }

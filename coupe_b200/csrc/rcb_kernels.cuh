@@ -321,7 +321,10 @@ __device__ __forceinline__ long long load_w1(const void *__restrict__ w, size_t 
 // child = (bin >= split_bin); only points in the one bin a refined split fell
 // into compare their coordinate with the split position.
 // ---------------------------------------------------------------------------
-constexpr uint32_t SB_REFINED = 1u << 16;  // flag in the split-bin word of the parent table
+// Split word of the per-parent table: T = (parent << kprev) + split_bin in the low 31 bits, so
+// that child = (previous idx word >= T); bit 31 set when the split was refined inside bin T,
+// whose points compare their coordinate with the split position instead.
+constexpr uint32_t SB_REFINED = 1u << 31;
 constexpr uint32_t TARGET_NONE = 0xFFFFFFFFu;
 
 struct SweepArgs {
@@ -360,12 +363,12 @@ __device__ __noinline__ uint32_t descend_exact(float x, float lo, float hi, int 
   return bin;
 }
 
-// Child (0 = left, 1 = right) of a point whose previous-level bin is b.
-__device__ __forceinline__ uint32_t child_of(uint32_t b, uint32_t sbword, const float *xp, size_t i,
+// Child (0 = left, 1 = right) of a point from its previous-level idx word.
+__device__ __forceinline__ uint32_t child_of(uint32_t pv, uint32_t sbword, const float *xp, size_t i,
                                              const float *split_ptr) {
-  const uint32_t sb = sbword & 0xFFFFu;
-  uint32_t child = b >= sb ? 1u : 0u;
-  if ((sbword & SB_REFINED) && b == sb) child = !(__ldg(xp + i) < __ldg(split_ptr)) ? 1u : 0u;
+  const uint32_t T = sbword & ~SB_REFINED;
+  uint32_t child = pv >= T ? 1u : 0u;
+  if ((sbword & SB_REFINED) && pv == T) child = !(__ldg(xp + i) < __ldg(split_ptr)) ? 1u : 0u;
   return child;
 }
 
@@ -378,7 +381,7 @@ __device__ __noinline__ uint32_t slot_exact(const SweepArgs &a, uint32_t pv, flo
   const float4 e = __ldg(&a.table[p]);
   uint32_t node = 0;
   if (!root)
-    node = 2 * p + child_of(pv & ((1u << a.kprev) - 1), __float_as_uint(e.w), a.xp, i, a.table_split + p);
+    node = 2 * p + child_of(pv, __float_as_uint(e.w), a.xp, i, a.table_split + p);
   return (node << a.k) + descend_exact(x, e.x, __ldg(a.table_hi + p), a.k);
 }
 
@@ -398,6 +401,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void reds_min(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 // min into [addr] only when it lowers the value seen by a plain load first
 __device__ __forceinline__ void reds_min_if_lower(uint32_t addr, uint32_t key) {
@@ -565,10 +571,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   const double scale = (WIN == WIN_F64) ? a.gp->scale : 1.0;
   const uint32_t lo_base = smem_addr(s_lo) + (SMEM ? (threadIdx.x & (ncopy - 1)) * cstride * 4 : 0);
   const uint32_t hi_off = nacc * 4, min_off = nacc * 8;
-  const uint32_t bmask = (1u << kprev) - 1;
   const bool vec = a.w_vec != 0;
   const bool narrow = ROOT && (WIN == WIN_I64 || WIN == WIN_F64) && a.w32_out != nullptr;
   bool wide = false;  // some i64 weight does not fit the narrowed i32 column
+  const uint32_t kbit = 1u << k;
 
   const size_t n = a.n;
   const size_t nfull = n / 4;  // groups of four points without bounds checks
@@ -585,20 +591,20 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     const float x[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
     long long w[4];
     cur.w.get(scale, w);
-    uint32_t slot[4];
-    uint32_t slow = 0;
+    uint32_t slot[4], base[4];
+    uint32_t slow = 0;  // points that need the exact descend (slot_exact)
+    uint32_t hit = 0;   // points in the bin their parent's refined split fell into
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t p = pv[j] >> kprev;
       const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
-      uint32_t node = 0;
-      if (!ROOT) {  // child = (bin >= split bin) unless the parent's split was refined inside this bin
-        const uint32_t sbword = __float_as_uint(e.w);
-        const int d = (int)(pv[j] & bmask) - (int)(sbword & 0xFFFFu);
-        bool right = d >= 0;
-        if (d == 0 && (sbword & SB_REFINED))  // the bin the parent's refined split fell into
-          right = !(__ldg(a.xp + i0 + j) < (TSM ? s_split[p] : __ldg(a.table_split + p)));
-        node = 2 * p + (right ? 1u : 0u);
+      base[j] = 0;
+      if (!ROOT) {  // child = (previous idx >= threshold) unless the parent's split was refined in this bin
+        const uint32_t tw = __float_as_uint(e.w);
+        const uint32_t T = tw & ~SB_REFINED;
+        base[j] = p << (k + 1);
+        if (pv[j] >= T) base[j] |= kbit;
+        if (pv[j] == T && (tw & SB_REFINED)) hit |= 1u << j;
       }
       // bin = floor((x - lo) * 2^k / width), trusted when x is provably away from every
       // bin boundary (fast_bin_params); floor by adding 2^23 rounding down
@@ -606,8 +612,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       const float tf = __fadd_rd(t, 8388608.f);
       const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
       if (!(fabsf(fr - 0.5f) < e.z)) slow |= 1u << j;
-      slot[j] = (node << k) + (__float_as_uint(tf) & 0x7FFFFFu);
+      slot[j] = __float_as_uint(tf) & 0x7FFFFFu;
     }
+    if (!ROOT && hit) {  // compare the previous-axis coordinate with the refined split position
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (hit & (1u << j)) {
+          const uint32_t p = pv[j] >> kprev;
+          const float split = TSM ? s_split[p] : __ldg(a.table_split + p);
+          base[j] = (p << (k + 1)) | (!(__ldg(a.xp + i0 + j) < split) ? kbit : 0u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) slot[j] += base[j];
     if (slow) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -620,10 +637,39 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       if (WIN == WIN_I64)
         wide = wide || w[0] != (int)w[0] || w[1] != (int)w[1] || w[2] != (int)w[2] || w[3] != (int)w[3];
     }
+    if (SMEM) {
+      // four sums, then one rarely taken branch for the carries and one for the minima
+      uint32_t addr[4], key[4];
+      int hinc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (SMEM) accumulate_smem<WIN>(lo_base + slot[j] * 4, hi_off, min_off, w[j], f2key(x[j]));
-      else accumulate_global(a.hist_w, a.hist_min, slot[j], w[j], f2key(x[j]));
+      for (int j = 0; j < 4; ++j) {
+        addr[j] = lo_base + slot[j] * 4;
+        key[j] = f2key(x[j]);
+        if (WIN == WIN_CONST) {
+          reds_add(addr[j], 1u);  // a block sees fewer than 2^32 points: the count cannot wrap
+          hinc[j] = 0;
+        } else {
+          // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
+          const uint32_t wlo = (uint32_t)w[j];
+          const uint32_t old = atoms_add(addr[j], wlo);
+          hinc[j] = (int)(w[j] >> 32) + (old > ~wlo ? 1 : 0);  // + carry out of the low word
+        }
+      }
+      if (WIN != WIN_CONST && (hinc[0] | hinc[1] | hinc[2] | hinc[3])) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (hinc[j]) reds_add(addr[j] + hi_off, (uint32_t)hinc[j]);
+      }
+      bool lower = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lower = lower || key[j] < lds_u32(addr[j] + min_off);
+      if (lower) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reds_min(addr[j] + min_off, key[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) accumulate_global(a.hist_w, a.hist_min, slot[j], w[j], f2key(x[j]));
     }
     cur = nxt;
     g = gn;
@@ -1030,7 +1076,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   long long weight_left = 0;
   bool left_alive = false, right_alive = false;
   // split-bin word handed to the next level: first dense-pass bin on the right of the cut
-  uint32_t sbword = a.first ? 0u : (ns.sb | SB_REFINED);
+  uint32_t sbword = a.first ? 0u : (ns.sb | SB_REFINED);  // bin part; the node prefix is added below
   uint32_t t = 1;
   for (int depth = 0; depth < k; ++depth) {
     const float st = midpoint_f32(lo, hi);  // :472
@@ -1104,7 +1150,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   {
     float inv, hme;
     fast_bin_params(ns.box_lo[next_axis], ns.box_hi[next_axis], a.k_next, inv, hme);
-    a.table_next[p] = make_float4(ns.box_lo[next_axis], inv, hme, __uint_as_float(sbword));
+    a.table_next[p] = make_float4(ns.box_lo[next_axis], inv, hme, __uint_as_float(sbword + (p << a.k0)));
     a.table_next_hi[p] = ns.box_hi[next_axis];
     a.table_next_split[p] = split_pos;
   }
@@ -1158,7 +1204,6 @@ emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp
   const uint32_t off = gp->leaf_min;
   const size_t ngroups = (n + 3) / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const uint32_t bmask = (1u << klast) - 1;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
     const size_t i0 = g * 4;
     Idx4<IDX> vv;
@@ -1171,7 +1216,7 @@ emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp
       if (i0 + j >= n) continue;
       const uint32_t p = v[j] >> klast;
       const uint32_t sbword = __float_as_uint(__ldg(&table[p]).w);
-      r[j] = (unsigned long long)(2 * p + child_of(v[j] & bmask, sbword, xp, i0 + j, table_split + p) - off);
+      r[j] = (unsigned long long)(2 * p + child_of(v[j], sbword, xp, i0 + j, table_split + p) - off);
     }
     if (i0 + 4 <= n && out_vec) {
       __stcs(reinterpret_cast<ulonglong2 *>(out + i0), make_ulonglong2(r[0], r[1]));
