@@ -30,12 +30,12 @@ class Stats(C.Structure):
     _fields_ = [("n_local", C.c_uint64), ("n_global", C.c_uint64), ("levels", C.c_uint32),
                 ("dense_sweeps", C.c_uint32), ("refine_sweeps", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("collectives", C.c_uint32),
-                ("weight_shift", C.c_int32), ("host_syncs", C.c_uint32), ("reserved", C.c_uint32),
+                ("weight_shift", C.c_int32), ("host_syncs", C.c_uint32), ("flag_waits", C.c_uint32),
                 ("matrix", C.c_double * 9), ("dense_sweep_ms", C.c_double),
                 ("refine_sweep_ms", C.c_double)]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("matrix", "reserved")}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "matrix"}
         d["matrix"] = list(self.matrix)
         return d
 

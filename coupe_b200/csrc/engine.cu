@@ -21,7 +21,8 @@ namespace {
 
 using namespace cb;
 
-constexpr int MAX_LEVELS = 20;  // 2^20 parts; node tables are replicated on every GPU
+constexpr int MAX_LEVELS = 20;
+constexpr uint64_t FLAG_SLOTS = 256;  // passes in flight are at most a handful  // 2^20 parts; node tables are replicated on every GPU
 
 struct CudaFail {
   cudaError_t err;
@@ -194,6 +195,9 @@ struct coupe_b200_ctx {
       tsp_a, tsp_b, target, rtable, gp,
       tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
   uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
+  volatile unsigned long long *h_flags = nullptr;  // mapped pinned: one word per pass, written by the GPU
+  unsigned long long *d_flags = nullptr;           // device view of h_flags
+  uint64_t flag_seq = 0;
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -532,10 +536,35 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const size_t fixed = (size_t)REFINE_QBYTES + (rts ? rt_bytes : 0) + 64;
     return (uint32_t)std::min<size_t>((size_t)1 << c->nb_smem_log2, (c->max_smem - fixed) / 12);
   };
+  // ---- level loop -----------------------------------------------------------------
+  // No stream synchronisation inside: the rank kernel that ends every pass writes the
+  // number of undecided nodes to mapped pinned host memory and the host polls that word.
+  // The first pass of level l+1 (and the final emit) is enqueued BEFORE the host knows
+  // whether level l needs refinement; its kernels return at once when it does
+  // (gp->unresolved != 0) and the pass is enqueued again after the refinement.
+  const uint32_t *guard_ptr = &gp->unresolved;
   uint32_t w_wide = 0;
-  auto run_walk = [&](int level, int k, int k0, int first, uint32_t rank_limit) {
+  uint64_t seq = c->flag_seq;
+  auto flag_slot = [&](uint64_t s) { return s % FLAG_SLOTS; };
+  auto wait_flag = [&](uint64_t s) -> uint32_t {
+    volatile unsigned long long *f = c->h_flags + flag_slot(s);
+    unsigned long long v;
+    for (uint64_t spin = 0; (v = *f) == 0; ++spin) {
+      if ((spin & 0xFFF) == 0xFFF) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q != cudaSuccess && q != cudaErrorNotReady) throw CudaFail{q, "cudaStreamQuery (flag wait)"};
+        if (q == cudaSuccess && *f == 0) throw CudaFail{cudaErrorUnknown, "pass ended without its flag"};
+      }
+    }
+    S.flag_waits += 1;
+    if (v & FLAG_ABORTED) throw CudaFail{cudaErrorUnknown, "waited on an aborted pass"};
+    w_wide = (uint32_t)(v >> 32) & 1u;
+    return (uint32_t)v;
+  };
+  // walk + rank of one pass; returns the sequence number of its flag
+  auto enqueue_walk = [&](int level, int k, int k0, int first, uint32_t rank_limit, const uint32_t *guard) {
     WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
-                tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit,
+                tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
                 plan_first(c, level + 1).k};
     const size_t bytes = ((size_t)2 << k) * 12;
     const uint32_t nodes = 1u << level;
@@ -544,22 +573,19 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     bool rts_;
     size_t rtb_;
+    const uint64_t s = seq++;
+    c->h_flags[flag_slot(s)] = 0;
     rank_unresolved_kernel<<<1, 1024, 0, st>>>(target, nodes, node_rt, rtable, rfast,
-                                               refine_cap(level, rts_, rtb_), c->kmax_refine, gp);
+                                               refine_cap(level, rts_, rtb_), c->kmax_refine, gp, guard,
+                                               c->d_flags + flag_slot(s));
     R.launched(2);
-    CU(cudaMemcpyAsync(c->h_pinned, &gp->unresolved, 8, cudaMemcpyDeviceToHost, st));
-    R.sync();
-    w_wide = c->h_pinned[1];
-    return c->h_pinned[0];
+    return s;
   };
-
-  int kprev = 0;
-  for (int level = 0; level < L; ++level) {
+  // the dense first pass of `level`; kprev = bins of the level before
+  auto enqueue_first_pass = [&](int level, int kprev, const uint32_t *guard) {
     const int axis = level % D, prev_axis = (level + D - 1) % D;
-    // ---- dense first pass ----------------------------------------------------
     const FirstPlan plan = plan_first(c, level);
     const int k = plan.k;
-    const bool smem = plan.smem;
     const uint32_t nb = 1u << (level + k);
     SweepArgs sa{};
     sa.n = n;
@@ -569,6 +595,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.w = wp;
     sa.w32_out = level == 0 ? w32 : nullptr;
     sa.gp = gp;
+    sa.guard = guard;
     sa.table = tab_cur;
     sa.table_hi = thi_cur;
     sa.table_split = tsp_cur;
@@ -581,84 +608,118 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.kprev = kprev;
     sa.copies_log2 = plan.copies_log2;
     sa.w_vec = ((uintptr_t)wp % 16) == 0;
-    if (!smem) {
-      fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb);
+    if (!plan.smem) {
+      fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb, guard);
       R.launched();
     }
     time_begin(0);
-    launch_sweep_any(win, level == 0, smem, plan.table_in_smem, idx16, sweep_grid, plan.bytes, st, sa);
+    launch_sweep_any(win, level == 0, plan.smem, plan.table_in_smem, idx16, sweep_grid, plan.bytes, st, sa);
     time_end();
     R.launched();
     S.dense_sweeps += 1;
-    if (smem) {
+    if (plan.smem) {
       reduce_partials_kernel<<<(nb + 31) / 32, 256, 0, st>>>(sa.part_w, sa.part_min, sweep_grid, nb,
-                                                             hist_w, hist_min);
+                                                             hist_w, hist_min, guard);
       R.launched();
     }
     R.allreduce(hist_w, nb, ncclUint64, ncclSum);
     R.allreduce(hist_min, nb, ncclUint32, ncclMin);
-    uint32_t unresolved = run_walk(level, k, k, 1, 0);
-    if (level == 0 && w32) {  // from here on the sweeps read the narrowed weights
-      if (c->world > 1 && wtype == WT_I64) {  // every rank must take the same path
+    return enqueue_walk(level, k, k, 1, 0, guard);
+  };
+  auto enqueue_refine_round = [&](int level, int k0, uint32_t unresolved) {
+    // ranked histograms of as many undecided nodes as shared memory holds, 2^kr bins each
+    const int axis = level % D;
+    bool rts;
+    size_t rt_bytes;
+    const uint32_t cap = refine_cap(level, rts, rt_bytes);
+    const int kr = refine_bits(unresolved, cap, c->kmax_refine);
+    const uint32_t limit = std::min<uint32_t>(unresolved, cap >> kr);
+    const uint32_t nslots = limit << kr;
+    const size_t rbytes = (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
+    RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
+                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts};
+    time_begin(1);
+    switch (win) {
+      case WIN_I32: launch_refine<WIN_I32>(idx16, sweep_grid, rbytes, st, ra); break;
+      case WIN_I64: launch_refine<WIN_I64>(idx16, sweep_grid, rbytes, st, ra); break;
+      default: launch_refine<WIN_CONST>(idx16, sweep_grid, rbytes, st, ra); break;
+    }
+    time_end();
+    reduce_partials_kernel<<<(nslots + 31) / 32, 256, 0, st>>>(ra.part_w, ra.part_min, sweep_grid,
+                                                               nslots, hist_w, hist_min, nullptr);
+    R.launched(2);
+    S.refine_sweeps += 1;
+    R.allreduce(hist_w, nslots, ncclUint64, ncclSum);
+    R.allreduce(hist_min, nslots, ncclUint32, ncclMin);
+    return enqueue_walk(level, kr, k0, 0, limit, nullptr);
+  };
+  auto advance_level = [&]() {
+    std::swap(cur, nxt);
+    std::swap(tab_cur, tab_next);
+    std::swap(thi_cur, thi_next);
+    std::swap(tsp_cur, tsp_next);
+  };
+  auto enqueue_emit = [&](int klast, const uint32_t *guard) {
+    const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(part_dev);
+    const int out_vec = ((uintptr_t)part_dev % 16) == 0;
+    if (idx16)
+      emit_kernel<uint16_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+    else
+      emit_kernel<uint32_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+    R.launched();
+  };
+
+  // cur/tab_cur always describe the level whose pass is enqueued next
+  uint64_t pending = enqueue_first_pass(0, 0, nullptr);  // flag of the pass of `level`
+  for (int level = 0; level < L; ++level) {
+    const int k = plan_first(c, level).k;
+    // i64 weights: which column the later sweeps read is only known after the root pass
+    const bool can_speculate = !(level == 0 && w32 && wtype == WT_I64);
+    advance_level();
+    bool speculated = false;
+    uint64_t next_pending = 0;
+    if (can_speculate) {
+      if (level == 0 && w32) {  // f64 weights: always narrowed
+        win = WIN_I32;
+        wp = w32;
+      }
+      if (level + 1 < L) next_pending = enqueue_first_pass(level + 1, k, guard_ptr);
+      else enqueue_emit(k, guard_ptr);
+      speculated = true;
+    }
+    uint32_t unresolved = wait_flag(pending);
+    if (level == 0 && w32 && wtype == WT_I64) {
+      if (c->world > 1) {  // every rank must take the same path
         R.allreduce(&gp->w_wide, 1, ncclUint32, ncclMax);
         CU(cudaMemcpyAsync(c->h_pinned, &gp->w_wide, 4, cudaMemcpyDeviceToHost, st));
         R.sync();
         w_wide = c->h_pinned[0];
       }
-      if (wtype == WT_F64 || !w_wide) {
+      if (!w_wide) {
         win = WIN_I32;
         wp = w32;
       }
     }
-
-    // ---- sparse refinement passes while some bisection is undecided ----------
-    int guard = 0;
-    while (unresolved > 0) {
-      if (++guard > 100000) return COUPE_ERR_CRASH;  // cannot happen: f32 brackets shrink
-      // ranked histograms of as many undecided nodes as shared memory holds, 2^kr bins each
-      bool rts;
-      size_t rt_bytes;
-      const uint32_t cap = refine_cap(level, rts, rt_bytes);
-      const int kr = refine_bits(unresolved, cap, c->kmax_refine);
-      const uint32_t limit = std::min<uint32_t>(unresolved, cap >> kr);
-      const uint32_t nslots = limit << kr;
-      const size_t rbytes =
-          (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
-      RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
-                    c->part_min.as<uint32_t>(), nslots, limit, level, kr, k, rts};
-      time_begin(1);
-      switch (win) {
-        case WIN_I32: launch_refine<WIN_I32>(idx16, sweep_grid, rbytes, st, ra); break;
-        case WIN_I64: launch_refine<WIN_I64>(idx16, sweep_grid, rbytes, st, ra); break;
-        default: launch_refine<WIN_CONST>(idx16, sweep_grid, rbytes, st, ra); break;
+    if (unresolved > 0) {
+      // the optimistic pass (if any) returned at once on the device; refine this level, then redo it
+      if (speculated && level + 1 < L) S.dense_sweeps -= 1;
+      advance_level();  // back to this level's tables
+      int guard = 0;
+      while (unresolved > 0) {
+        if (++guard > 100000) return COUPE_ERR_CRASH;  // cannot happen: f32 brackets shrink
+        unresolved = wait_flag(enqueue_refine_round(level, k, unresolved));
       }
-      time_end();
-      reduce_partials_kernel<<<(nslots + 31) / 32, 256, 0, st>>>(ra.part_w, ra.part_min, sweep_grid,
-                                                                 nslots, hist_w, hist_min);
-      R.launched(2);
-      S.refine_sweeps += 1;
-      R.allreduce(hist_w, nslots, ncclUint64, ncclSum);
-      R.allreduce(hist_min, nslots, ncclUint32, ncclMin);
-      unresolved = run_walk(level, kr, k, 0, limit);
+      advance_level();
+      speculated = false;
     }
-    std::swap(cur, nxt);
-    std::swap(tab_cur, tab_next);
-    std::swap(thi_cur, thi_next);
-    std::swap(tsp_cur, tsp_next);
-    kprev = k;
+    if (!speculated) {
+      if (level + 1 < L) next_pending = enqueue_first_pass(level + 1, k, nullptr);
+      else enqueue_emit(k, nullptr);
+    }
+    pending = next_pending;
   }
-
-  // ---- final ids -------------------------------------------------------------
-  {
-    const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
-    unsigned long long *out = reinterpret_cast<unsigned long long *>(part_dev);
-    const int out_vec = ((uintptr_t)part_dev % 16) == 0;
-    if (idx16)
-      emit_kernel<uint16_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, kprev, gp, out, out_vec);
-    else
-      emit_kernel<uint32_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, kprev, gp, out, out_vec);
-    R.launched();
-  }
+  c->flag_seq = seq;
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
   memcpy(&S.weight_shift, c->h_pinned, 4);
@@ -717,6 +778,13 @@ int coupe_b200_ctx_create(coupe_b200_ctx **out, int device) {
     c->max_smem = prop.sharedMemPerBlockOptin;
     CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pinned), 64 * sizeof(uint32_t) * 4,
                      cudaHostAllocDefault));
+    void *hf = nullptr;
+    CU(cudaHostAlloc(&hf, FLAG_SLOTS * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(hf, 0, FLAG_SLOTS * sizeof(unsigned long long));
+    c->h_flags = static_cast<volatile unsigned long long *>(hf);
+    void *df = nullptr;
+    CU(cudaHostGetDevicePointer(&df, hf, 0));
+    c->d_flags = static_cast<unsigned long long *>(df);
   } catch (const CudaFail &f) {
     fprintf(stderr, "coupe_b200: CUDA error %s at %s\n", cudaGetErrorString(f.err), f.what);
     delete c;
@@ -735,6 +803,7 @@ void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
                  &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
     b->release();
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->h_flags) cudaFreeHost(const_cast<unsigned long long *>(c->h_flags));
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   delete c;
 }

@@ -335,6 +335,7 @@ struct SweepArgs {
   const void *w;             // weights in the kernel's WIN format (null for WIN_CONST)
   int *w32_out;              // root level: narrowed i32 copy of i64 / f64 weights, or null
   GlobalParams *gp;
+  const uint32_t *guard;     // optimistic launch: return at once if *guard != 0 (previous level undecided)
   const float4 *table;       // per parent: {bracket lo, 2^k / width, 0.5 - eps, split-bin word}
   const float *table_hi;     // per parent: bracket hi (exact descend only)
   const float *table_split;  // per parent: split position (refined parents only)
@@ -543,6 +544,7 @@ struct Group4 {  // everything the sweep reads for four consecutive points
 template <int WIN, bool SMEM, bool ROOT, bool TSM, class IDX>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (a.guard && *a.guard != 0) return;
   const int k = a.k, level = a.level, kprev = a.kprev;
   const uint32_t nb = 1u << (level + k);  // bins of this level
   const int ncopy = 1 << a.copies_log2;
@@ -714,8 +716,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__restrict__ part_min,
                        int nblocks, uint32_t nb, unsigned long long *__restrict__ hist_w,
-                       uint32_t *__restrict__ hist_min) {
+                       uint32_t *__restrict__ hist_min, const uint32_t *guard) {
   __shared__ unsigned long long s_w[8][32];
+  if (guard && *guard != 0) return;
   __shared__ uint32_t s_m[8][32];
   const uint32_t lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const uint32_t i = blockIdx.x * 32 + lane;
@@ -741,7 +744,8 @@ reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__r
 }
 
 __global__ void __launch_bounds__(256)
-fill_hist_kernel(unsigned long long *hist_w, uint32_t *hist_min, uint32_t nb) {
+fill_hist_kernel(unsigned long long *hist_w, uint32_t *hist_min, uint32_t nb, const uint32_t *guard) {
+  if (guard && *guard != 0) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nb) {
     hist_w[i] = 0;
@@ -901,15 +905,25 @@ __host__ __device__ inline int refine_bits(uint32_t unresolved, uint32_t cap, in
   return kr;
 }
 
+constexpr unsigned long long FLAG_VALID = 1ull << 63, FLAG_ABORTED = 1ull << 62;
+
 // Ranks the undecided nodes of a level in node order (identical on every GPU),
 // counts them and prepares their fast binning parameters: node_rt[p] =
 // {target idx, rank}, rfast[p] = {2^kr / width, 0.5 - eps}.
 __global__ void __launch_bounds__(1024)
 rank_unresolved_kernel(const uint32_t *__restrict__ target, uint32_t nodes, uint2 *__restrict__ node_rt,
                        const float4 *__restrict__ rtable, float2 *__restrict__ rfast, uint32_t cap,
-                       int kmax, GlobalParams *gp) {
+                       int kmax, GlobalParams *gp, const uint32_t *guard,
+                       volatile unsigned long long *host_flag) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_base;
+  if (guard && *guard != 0) {  // the whole pass was launched optimistically and did not run
+    if (threadIdx.x == 0) {
+      *host_flag = FLAG_ABORTED;
+      __threadfence_system();
+    }
+    return;
+  }
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -932,8 +946,6 @@ rank_unresolved_kernel(const uint32_t *__restrict__ target, uint32_t nodes, uint
     __syncthreads();
   }
   const uint32_t unresolved = s_base;
-  if (threadIdx.x == 0) gp->unresolved = unresolved;
-  if (unresolved == 0) return;
   const int kr = refine_bits(unresolved, cap, kmax);
   for (uint32_t p = threadIdx.x; p < nodes; p += blockDim.x) {
     if (target[p] == TARGET_NONE) continue;
@@ -941,6 +953,13 @@ rank_unresolved_kernel(const uint32_t *__restrict__ target, uint32_t nodes, uint
     float inv, hme;
     fast_bin_params(r.x, r.y, kr, inv, hme);
     rfast[p] = make_float2(inv, hme);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // the host polls this word (mapped pinned memory) instead of synchronising
+    gp->unresolved = unresolved;
+    __threadfence();
+    *host_flag = FLAG_VALID | ((unsigned long long)gp->w_wide << 32) | unresolved;
+    __threadfence_system();
   }
 }
 
@@ -995,12 +1014,14 @@ struct WalkArgs {
   int level, k, D, first, last_level, w_is_const;
   int k0;                    // bins of this level's dense pass
   uint32_t rank_limit;       // refinement: nodes ranked at or above were not swept this pass
+  const uint32_t *guard;     // optimistic launch: return at once if *guard != 0
   int k_next;                // bins of the next level's dense pass
 };
 
 template <int WT>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (a.guard && *a.guard != 0) return;
   const int k = a.k;
   const uint32_t nb = 1u << k;
   unsigned long long *wtree = reinterpret_cast<unsigned long long *>(smem_raw);  // heap, 2nb
@@ -1200,7 +1221,9 @@ template <class IDX>
 __global__ void __launch_bounds__(512)
 emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp,
             const float4 *__restrict__ table, const float *__restrict__ table_split, int klast,
-            const GlobalParams *__restrict__ gp, unsigned long long *__restrict__ out, int out_vec) {
+            const GlobalParams *__restrict__ gp, unsigned long long *__restrict__ out, int out_vec,
+            const uint32_t *guard) {
+  if (guard && *guard != 0) return;
   const uint32_t off = gp->leaf_min;
   const size_t ngroups = (n + 3) / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--tol", type=float, default=0.05)
     ap.add_argument("--w", default="f64", choices=["f64", "i64", "i32", "const"])
-    ap.add_argument("--dist", default="uniform", choices=["uniform", "gauss"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "gauss", "grid"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--opt", action="append", default=[])
     a = ap.parse_args()
@@ -27,9 +27,19 @@ def main():
     g.manual_seed(1)
     if a.dist == "uniform":
         pts = torch.rand((a.n, a.dim), dtype=torch.float64, device=dev, generator=g)
+    elif a.dist == "grid":  # hex-mesh cell centres in natural (x fastest) order, C3-like
+        nx, ny = 400, 500
+        nz = a.n // (nx * ny)
+        a.n = nx * ny * nz
+        i = torch.arange(a.n, device=dev)
+        pts = torch.stack([(i % nx).double() + 0.5, ((i // nx) % ny).double() + 0.5,
+                           (i // (nx * ny)).double() + 0.5], dim=1).contiguous()
+        del i
     else:
         pts = torch.randn((a.n, a.dim), dtype=torch.float64, device=dev, generator=g)
-    if a.w == "f64":
+    if a.w == "f64" and a.dist == "grid":  # weight-gen "linear,x,0,100"
+        w = (pts[:, 0] - 0.5) * (100.0 / 399.0)
+    elif a.w == "f64":
         w = torch.rand(a.n, dtype=torch.float64, device=dev, generator=g) + 0.5
     elif a.w == "i64":
         w = torch.randint(1, 100, (a.n,), dtype=torch.int64, device=dev, generator=g)
