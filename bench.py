@@ -131,6 +131,7 @@ def cpu_oracle_run(n_sample, steps, warmup, pts_np=None, w_np=None):
     from oracle import pyoracle
 
     pyoracle.build()
+    pyoracle.set_num_threads(len(os.sched_getaffinity(0)))  # all host cores, also under torchrun (OMP_NUM_THREADS=1)
     if pts_np is None:
         rng = np.random.default_rng(4)
         means = rng.random((16, DIM))

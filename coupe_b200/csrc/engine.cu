@@ -213,10 +213,10 @@ struct coupe_b200_ctx {
 
 namespace {
 
-size_t sweep_smem_bytes(int level, int k, int copies_log2, bool table_in_smem) {
-  const size_t nb = (size_t)1 << (level + k);
-  size_t b = (((nb + 1) * ((size_t)1 << copies_log2) * 12 + 15) / 16) * 16;
-  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
+size_t sweep_smem_bytes(int level, bool table_in_smem) {
+  // the three histogram arrays sit at fixed offsets (rcb_kernels.cuh: HIST_BYTES), the table after them
+  size_t b = HIST_BYTES;
+  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float));
   return b;
 }
 
@@ -296,13 +296,13 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
   p.table_in_smem = true;
   if (p.smem) {
     p.copies_log2 = std::min(5, c->nb_smem_log2 - (level + p.k));
-    p.bytes = sweep_smem_bytes(level, p.k, p.copies_log2, true);
+    p.bytes = sweep_smem_bytes(level, true);
     if (p.bytes > c->max_smem) p.smem = false;
   }
   if (!p.smem) {
     p.k = std::max(1, std::min(c->kmax_a, 17 - level));
     p.copies_log2 = 0;
-    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + sizeof(float));
+    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float));
     p.table_in_smem = tb <= 64 * 1024;
     p.bytes = p.table_in_smem ? tb : 0;
   }
@@ -366,7 +366,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->target.ensure(max_nodes * sizeof(uint32_t));
   c->node_rt.ensure(max_nodes * sizeof(uint2));
   c->rfast.ensure(max_nodes * sizeof(float2));
-  const bool narrow_w = w_dev && (wtype == WT_F64 || (wtype == WT_I64 && L > 1));
+  // i32 column read by the sweeps below the root: narrowed f64 / i64 weights, or an aligned copy
+  // of caller's i32 weights that are not 16-byte aligned
+  const bool narrow_w = w_dev && (wtype == WT_F64 || (wtype == WT_I64 && L > 1) ||
+                                  (wtype == WT_I32 && L > 1 && ((uintptr_t)w_dev % 16) != 0));
   if (narrow_w) c->w32.ensure(npad * sizeof(int));
   c->gp.ensure(sizeof(GlobalParams));
   c->mom_partial.ensure((size_t)c->num_sms * 8 * 16 * sizeof(double));
@@ -608,6 +611,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.kprev = kprev;
     sa.copies_log2 = plan.copies_log2;
     sa.w_vec = ((uintptr_t)wp % 16) == 0;
+    sa.one = 1;
     if (!plan.smem) {
       fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb, guard);
       R.launched();
@@ -637,7 +641,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const uint32_t nslots = limit << kr;
     const size_t rbytes = (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
     RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
-                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts};
+                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u};
     time_begin(1);
     switch (win) {
       case WIN_I32: launch_refine<WIN_I32>(idx16, sweep_grid, rbytes, st, ra); break;

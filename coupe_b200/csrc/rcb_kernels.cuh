@@ -321,10 +321,13 @@ __device__ __forceinline__ long long load_w1(const void *__restrict__ w, size_t 
 // child = (bin >= split_bin); only points in the one bin a refined split fell
 // into compare their coordinate with the split position.
 // ---------------------------------------------------------------------------
-// Split word of the per-parent table: T = (parent << kprev) + split_bin in the low 31 bits, so
-// that child = (previous idx word >= T); bit 31 set when the split was refined inside bin T,
-// whose points compare their coordinate with the split position instead.
-constexpr uint32_t SB_REFINED = 1u << 31;
+// Split word of the per-parent table: tw = (T << 1) | refined, T = (parent << kprev) + split_bin
+// = the first previous-level idx word on the right of the cut.  With q = 2 * idx + 1 the child is
+// (q >= tw) for either value of the flag, and q == tw singles out the points of bin T when the
+// split was refined inside that bin: they compare their coordinate with the split position.
+__host__ __device__ __forceinline__ uint32_t split_word(uint32_t T, bool refined) {
+  return (T << 1) | (refined ? 1u : 0u);
+}
 constexpr uint32_t TARGET_NONE = 0xFFFFFFFFu;
 
 struct SweepArgs {
@@ -346,6 +349,8 @@ struct SweepArgs {
   int level, k, kprev;
   int copies_log2;           // SMEM mode: 2^copies_log2 lane-private copies per block
   int w_vec;                 // weights are 16-byte aligned
+  uint32_t one;              // 1, from the host: a literal 1 turns `red.shared.add` into ATOMS.POPC.INC,
+                             // which is several times slower than ATOMS.ADD on scattered addresses
 };
 
 // Exact bin of x in the bracket [lo, hi]: k dyadic bisection steps with the
@@ -365,11 +370,11 @@ __device__ __noinline__ uint32_t descend_exact(float x, float lo, float hi, int 
 }
 
 // Child (0 = left, 1 = right) of a point from its previous-level idx word.
-__device__ __forceinline__ uint32_t child_of(uint32_t pv, uint32_t sbword, const float *xp, size_t i,
+__device__ __forceinline__ uint32_t child_of(uint32_t pv, uint32_t tw, const float *xp, size_t i,
                                              const float *split_ptr) {
-  const uint32_t T = sbword & ~SB_REFINED;
-  uint32_t child = pv >= T ? 1u : 0u;
-  if ((sbword & SB_REFINED) && pv == T) child = !(__ldg(xp + i) < __ldg(split_ptr)) ? 1u : 0u;
+  const uint32_t q = 2 * pv + 1;
+  uint32_t child = q >= tw ? 1u : 0u;
+  if (q == tw) child = !(__ldg(xp + i) < __ldg(split_ptr)) ? 1u : 0u;
   return child;
 }
 
@@ -421,9 +426,9 @@ __device__ __forceinline__ void reds_min_if_lower(uint32_t addr, uint32_t key) {
 // bytes further.
 template <int WIN>
 __device__ __forceinline__ void accumulate_smem(uint32_t lo_addr, uint32_t hi_off, uint32_t min_off,
-                                                long long w, uint32_t key) {
+                                                long long w, uint32_t key, uint32_t one) {
   if (WIN == WIN_CONST) {
-    reds_add(lo_addr, 1u);  // a block sees fewer than 2^32 points: the count cannot wrap
+    reds_add(lo_addr, one);  // a block sees fewer than 2^32 points: the count cannot wrap
   } else {
     // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
     const uint32_t wlo = (uint32_t)w;
@@ -540,6 +545,50 @@ struct Group4 {  // everything the sweep reads for four consecutive points
   }
 };
 
+// --- block-private histogram of the dense sweep ---------------------------------
+// Three word arrays at FIXED shared-memory offsets (so that the hot loop addresses them with
+// immediate offsets): low sum word, minimum coordinate (signed order-preserving key, SKEY_EMPTY if none),
+// high sum word.  Word index = (slot << copies_log2) + copy with copy = lane % copies: at
+// 32 copies every lane owns a bank and the atomics of a warp never conflict; with fewer
+// copies only the lanes that share a copy can.
+constexpr uint32_t HIST_WORDS_LOG2 = 14;
+constexpr uint32_t HIST_ARRAY_BYTES = 4u << HIST_WORDS_LOG2;  // 64 KB per array
+constexpr uint32_t HIST_MIN_OFF = HIST_ARRAY_BYTES, HIST_HI_OFF = 2 * HIST_ARRAY_BYTES;
+constexpr uint32_t HIST_BYTES = 3 * HIST_ARRAY_BYTES;
+constexpr int SKEY_EMPTY = 0x7FFFFFFF;
+
+// Order-preserving float -> SIGNED int key (two instructions); key ^ 0x80000000 is f2key().
+__device__ __forceinline__ int f2skey(float f) {
+  const int s = __float_as_int(f);
+  return s ^ ((s >> 31) & 0x7FFFFFFF);
+}
+// the minimum word of the slot whose low sum word is at lo_addr (offset folded into the load)
+__device__ __forceinline__ int lds_min_of(uint32_t lo_addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(lo_addr), "n"(HIST_MIN_OFF) : "memory");
+  return v;
+}
+__device__ __forceinline__ void reds_min_of(uint32_t lo_addr, int key) {
+  asm volatile("red.shared.min.s32 [%0+%1], %2;" ::"r"(lo_addr), "n"(HIST_MIN_OFF), "r"(key) : "memory");
+}
+
+// One point, general weights (negative ones included); lo_addr = address of the low sum word.
+template <int WIN>
+__device__ __forceinline__ void hist_add_generic(uint32_t lo_addr, long long w, float x, uint32_t one) {
+  if (WIN == WIN_CONST) {
+    reds_add(lo_addr, one);  // a block sees fewer than 2^32 points: the count cannot wrap
+  } else {
+    // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
+    const uint32_t wlo = (uint32_t)w;
+    const uint32_t old = atoms_add(lo_addr, wlo);
+    int hinc = (int)(w >> 32);
+    if (old > ~wlo) ++hinc;  // carry out of the low word
+    if (hinc != 0) reds_add(lo_addr + HIST_HI_OFF, (uint32_t)hinc);
+  }
+  const int key = f2skey(x);
+  if (key < lds_min_of(lo_addr)) reds_min_of(lo_addr, key);
+}
+
 // TSM: the per-parent table is staged in shared memory (always in SMEM mode).
 template <int WIN, bool SMEM, bool ROOT, bool TSM, class IDX>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_constant__ SweepArgs a) {
@@ -547,92 +596,102 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   if (a.guard && *a.guard != 0) return;
   const int k = a.k, level = a.level, kprev = a.kprev;
   const uint32_t nb = 1u << (level + k);  // bins of this level
-  const int ncopy = 1 << a.copies_log2;
-  const uint32_t cstride = nb + 1;        // copies are skewed by one bank
-  const uint32_t nacc = SMEM ? cstride * (uint32_t)ncopy : 0;
+  const int clog = a.copies_log2;
+  const uint32_t nwords = SMEM ? (nb << clog) : 0;  // words in use of each histogram array
   uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *s_hi = s_lo + nacc;
-  uint32_t *s_min = s_hi + nacc;
-  float4 *s_table = reinterpret_cast<float4 *>(smem_raw + (((size_t)nacc * 12 + 15) / 16) * 16);
+  uint32_t *s_min = reinterpret_cast<uint32_t *>(smem_raw + HIST_MIN_OFF);
+  uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw + HIST_HI_OFF);
+  float4 *s_table = reinterpret_cast<float4 *>(smem_raw + (SMEM ? HIST_BYTES : 0));
   const int nparents = 1 << (level > 0 ? level - 1 : 0);
   float *s_split = reinterpret_cast<float *>(s_table + (TSM ? nparents : 0));
+  float *s_thi = s_split + (TSM ? nparents : 0);
   if (SMEM) {
-    const uint32_t total = cstride * (uint32_t)ncopy;
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) {
       s_lo[i] = 0;
       s_hi[i] = 0;
-      s_min[i] = KEY_EMPTY;
+      s_min[i] = (uint32_t)SKEY_EMPTY;
     }
   }
   if (TSM)
     for (int i = threadIdx.x; i < nparents; i += blockDim.x) {
       s_table[i] = a.table[i];
       s_split[i] = a.table_split[i];
+      s_thi[i] = a.table_hi[i];
     }
   __syncthreads();
   const double scale = (WIN == WIN_F64) ? a.gp->scale : 1.0;
-  const uint32_t lo_base = smem_addr(s_lo) + (SMEM ? (threadIdx.x & (ncopy - 1)) * cstride * 4 : 0);
-  const uint32_t hi_off = nacc * 4, min_off = nacc * 8;
-  const bool vec = a.w_vec != 0;
-  const bool narrow = ROOT && (WIN == WIN_I64 || WIN == WIN_F64) && a.w32_out != nullptr;
+  // address of this lane's copy of slot 0; slot s sits slot_stride bytes * s further
+  const uint32_t lo_base = smem_addr(s_lo) + (SMEM ? (threadIdx.x & ((1u << clog) - 1)) * 4 : 0);
+  const uint32_t slot_stride = 4u << clog;
+  // below the root an i32 column is always 16-byte aligned (the caller's own when it is, else the engine's copy)
+  const bool vec = (ROOT || WIN == WIN_I64) ? a.w_vec != 0 : true;
+  const bool narrow = ROOT && WIN != WIN_CONST && a.w32_out != nullptr;
   bool wide = false;  // some i64 weight does not fit the narrowed i32 column
   const uint32_t kbit = 1u << k;
+  // slot = (parent << (k+1)) + child * 2^k + bin; the bin comes out of the float trick below as
+  // bits(tf) = 0x4B000000 + bin, so the constant is folded into the child term
+  const uint32_t sel_left = 0u - 0x4B000000u, sel_right = kbit - 0x4B000000u;
 
   const size_t n = a.n;
   const size_t nfull = n / 4;  // groups of four points without bounds checks
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Group4<WIN, ROOT, IDX> cur, nxt;
-  if (g < nfull) cur.load(a, g * 4, vec);
-  while (g < nfull) {
-    const size_t gn = g + stride;
-    if (gn < nfull) nxt.load(a, gn * 4, vec);  // in flight while this group is processed
+
+  auto process = [&](const Group4<WIN, ROOT, IDX> &cur, size_t g) {
     const size_t i0 = g * 4;
     uint32_t pv[4] = {0, 0, 0, 0};
     if (!ROOT) cur.pv.get(pv);
     const float x[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
-    long long w[4];
-    cur.w.get(scale, w);
-    uint32_t slot[4], base[4];
-    uint32_t slow = 0;  // points that need the exact descend (slot_exact)
-    uint32_t hit = 0;   // points in the bin their parent's refined split fell into
+    uint32_t slot[4], pk[4], sel[4];
+    bool slow = false;  // some point is within rounding of a bin boundary
+    bool hit = false;   // some point sits in the bin its parent's refined split fell into
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t p = pv[j] >> kprev;
       const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
-      base[j] = 0;
-      if (!ROOT) {  // child = (previous idx >= threshold) unless the parent's split was refined in this bin
-        const uint32_t tw = __float_as_uint(e.w);
-        const uint32_t T = tw & ~SB_REFINED;
-        base[j] = p << (k + 1);
-        if (pv[j] >= T) base[j] |= kbit;
-        if (pv[j] == T && (tw & SB_REFINED)) hit |= 1u << j;
+      sel[j] = sel_left;
+      if (!ROOT) {  // child = (2 idx + 1 >= split word); equality marks the refined bin
+        const uint32_t tw = __float_as_uint(e.w), q = 2 * pv[j] + 1;
+        sel[j] = q >= tw ? sel_right : sel_left;
+        hit = hit || q == tw;
       }
       // bin = floor((x - lo) * 2^k / width), trusted when x is provably away from every
       // bin boundary (fast_bin_params); floor by adding 2^23 rounding down
       const float t = __fmul_rn(__fsub_rn(x[j], e.x), e.y);
       const float tf = __fadd_rd(t, 8388608.f);
       const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
-      if (!(fabsf(fr - 0.5f) < e.z)) slow |= 1u << j;
-      slot[j] = __float_as_uint(tf) & 0x7FFFFFu;
+      slow = slow || !(fabsf(fr - 0.5f) < e.z);
+      pk[j] = p << (k + 1);
+      slot[j] = __float_as_uint(tf);
     }
-    if (!ROOT && hit) {  // compare the previous-axis coordinate with the refined split position
+    if (!ROOT && hit) {  // the points of a refined bin compare their previous-axis coordinate with the split
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (hit & (1u << j)) {
-          const uint32_t p = pv[j] >> kprev;
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t p = pv[j] >> kprev;
+        const uint32_t tw = __float_as_uint(TSM ? s_table[p].w : __ldg(&a.table[p]).w);
+        if (2 * pv[j] + 1 == tw) {
           const float split = TSM ? s_split[p] : __ldg(a.table_split + p);
-          base[j] = (p << (k + 1)) | (!(__ldg(a.xp + i0 + j) < split) ? kbit : 0u);
+          sel[j] = !(__ldg(a.xp + i0 + j) < split) ? sel_right : sel_left;
         }
+      }
+    }
+    if (slow) {  // rare: redo the test per point, exact k-step descend where it fails
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t p = pv[j] >> kprev;
+        const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
+        const float t = __fmul_rn(__fsub_rn(x[j], e.x), e.y);
+        const float tf = __fadd_rd(t, 8388608.f);
+        const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
+        if (!(fabsf(fr - 0.5f) < e.z))
+          slot[j] = 0x4B000000u + descend_exact(x[j], e.x, TSM ? s_thi[p] : __ldg(a.table_hi + p), k);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) slot[j] += base[j];
-    if (slow) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (slow & (1u << j)) slot[j] = slot_exact(a, pv[j], x[j], i0 + j, ROOT);
-    }
+    for (int j = 0; j < 4; ++j) slot[j] += pk[j] + sel[j];
     Idx4<IDX>::store(a.idx, i0, slot);
+    long long w[4];
+    cur.w.get(scale, w);
     if (narrow) {
       __stcs(reinterpret_cast<int4 *>(a.w32_out + i0),
              make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
@@ -640,40 +699,73 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
         wide = wide || w[0] != (int)w[0] || w[1] != (int)w[1] || w[2] != (int)w[2] || w[3] != (int)w[3];
     }
     if (SMEM) {
-      // four sums, then one rarely taken branch for the carries and one for the minima
-      uint32_t addr[4], key[4];
-      int hinc[4];
+      uint32_t addr[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        addr[j] = lo_base + slot[j] * 4;
-        key[j] = f2key(x[j]);
-        if (WIN == WIN_CONST) {
-          reds_add(addr[j], 1u);  // a block sees fewer than 2^32 points: the count cannot wrap
-          hinc[j] = 0;
-        } else {
-          // 64-bit sum kept as two 32-bit words: shared memory has no native 64-bit add
+      for (int j = 0; j < 4; ++j) addr[j] = lo_base + slot[j] * slot_stride;
+      if (WIN == WIN_CONST) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reds_add(addr[j], a.one);  // a block sees fewer than 2^32 points
+      } else if (((w[0] | w[1] | w[2] | w[3]) >> 32) == 0) {
+        // four non-negative weights below 2^32 (the common case): one returning add each, the
+        // carries out of the low words summed through the carry flag
+        uint32_t old[4], carries;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) old[j] = atoms_add(addr[j], (uint32_t)w[j]);
+        asm("{\n\t.reg .u32 t;\n\t"
+            "add.cc.u32 t, %1, %5;\n\t addc.u32 %0, 0, 0;\n\t"
+            "add.cc.u32 t, %2, %6;\n\t addc.u32 %0, %0, 0;\n\t"
+            "add.cc.u32 t, %3, %7;\n\t addc.u32 %0, %0, 0;\n\t"
+            "add.cc.u32 t, %4, %8;\n\t addc.u32 %0, %0, 0;\n\t}"
+            : "=r"(carries)
+            : "r"(old[0]), "r"(old[1]), "r"(old[2]), "r"(old[3]), "r"((uint32_t)w[0]), "r"((uint32_t)w[1]),
+              "r"((uint32_t)w[2]), "r"((uint32_t)w[3]));
+        if (carries) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (old[j] > ~(uint32_t)w[j]) reds_add(addr[j] + HIST_HI_OFF, a.one);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           const uint32_t wlo = (uint32_t)w[j];
           const uint32_t old = atoms_add(addr[j], wlo);
-          hinc[j] = (int)(w[j] >> 32) + (old > ~wlo ? 1 : 0);  // + carry out of the low word
+          int hinc = (int)(w[j] >> 32);
+          if (old > ~wlo) ++hinc;
+          if (hinc != 0) reds_add(addr[j] + HIST_HI_OFF, (uint32_t)hinc);
         }
       }
-      if (WIN != WIN_CONST && (hinc[0] | hinc[1] | hinc[2] | hinc[3])) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (hinc[j]) reds_add(addr[j] + hi_off, (uint32_t)hinc[j]);
-      }
+      // running minimum: one plain load and compare per point; a warp takes the update branch
+      // often (some lane lowers some minimum), so the branch is four fire-and-forget mins
+      int key[4];
       bool lower = false;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) lower = lower || key[j] < lds_u32(addr[j] + min_off);
+      for (int j = 0; j < 4; ++j) {
+        key[j] = f2skey(x[j]);
+        lower = lower || key[j] < lds_min_of(addr[j]);
+      }
       if (lower) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) reds_min(addr[j] + min_off, key[j]);
+        for (int j = 0; j < 4; ++j) reds_min_of(addr[j], key[j]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) accumulate_global(a.hist_w, a.hist_min, slot[j], w[j], f2key(x[j]));
     }
-    cur = nxt;
+  };
+
+  // two register sets used in turn: the loads of the next group are in flight while the
+  // current one is processed
+  Group4<WIN, ROOT, IDX> ga, gb;
+  if (g < nfull) ga.load(a, g * 4, vec);
+  while (g < nfull) {
+    size_t gn = g + stride;
+    if (gn < nfull) gb.load(a, gn * 4, vec);
+    process(ga, g);
+    g = gn;
+    if (g >= nfull) break;
+    gn = g + stride;
+    if (gn < nfull) ga.load(a, gn * 4, vec);
+    process(gb, g);
     g = gn;
   }
   // tail: the last n % 4 points, one thread
@@ -688,7 +780,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
         a.w32_out[i] = (int)w;
         if (WIN == WIN_I64) wide = wide || w != (int)w;
       }
-      if (SMEM) accumulate_smem<WIN>(lo_base + slot * 4, hi_off, min_off, w, f2key(x));
+      if (SMEM) hist_add_generic<WIN>(lo_base + slot * slot_stride, w, x, a.one);
       else accumulate_global(a.hist_w, a.hist_min, slot, w, f2key(x));
     }
   }
@@ -697,13 +789,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     __syncthreads();
     long long *pw = a.part_w + (size_t)blockIdx.x * nb;
     uint32_t *pm = a.part_min + (size_t)blockIdx.x * nb;
+    const int ncopy = 1 << clog;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
       unsigned long long acc = 0;
       uint32_t m = KEY_EMPTY;
       for (int c = 0; c < ncopy; ++c) {
-        const uint32_t s = c * cstride + i;
+        const uint32_t s = (i << clog) + ((c + threadIdx.x) & (ncopy - 1));  // rotated: fewer bank conflicts
         acc += ((unsigned long long)s_hi[s] << 32) + s_lo[s];
-        m = min(m, s_min[s]);
+        m = min(m, s_min[s] ^ 0x80000000u);  // signed key -> unsigned key, SKEY_EMPTY -> KEY_EMPTY
       }
       pw[i] = (long long)acc;
       pm[i] = m;
@@ -774,23 +867,50 @@ struct RefineArgs {
   uint32_t rank_limit;     // nodes ranked at or above wait for a later pass
   int level, k, k0;        // k0: bins of the dense pass (idx = (node << k0) + bin)
   int rt_in_smem;
+  uint32_t one;            // 1, from the host (see SweepArgs::one)
 };
 
 constexpr int REFINE_BATCH = 64;                   // matches a warp lets build up before it drains them
-constexpr int REFINE_QCAP = REFINE_BATCH + 4 * 32;  // + what one warp iteration can add
-constexpr int REFINE_QBYTES = (SWEEP_THREADS / 32) * REFINE_QCAP * 8;
+constexpr int REFINE_QCAP = REFINE_BATCH + 8 * 32;  // + what one warp iteration can add
+constexpr int REFINE_QBYTES = (SWEEP_THREADS / 32) * REFINE_QCAP * 4;
 
-// Per warp, two phases: (1) every lane tests its four idx words against the
-// per-node targets and appends the matches to the warp's queue in shared
-// memory (a warp scan assigns the places, no atomics, no block barrier);
-// (2) once a batch has built up the warp drains it with every lane busy.
-// Matches are a few percent of the points, so without the queue nearly every
-// warp would run the expensive branch for one or two lanes at a time.
+// One 16-byte load of idx words per lane and iteration: 8 points (u16) or 4 (u32).
+template <class IDX>
+struct IdxVec;
+template <>
+struct IdxVec<uint16_t> {
+  static constexpr int N = 8;
+  uint4 v;
+  __device__ __forceinline__ void load(const void *p, size_t g) {
+    v = __ldcs(reinterpret_cast<const uint4 *>(p) + g);
+  }
+  __device__ __forceinline__ void get(uint32_t (&o)[8]) const {
+    o[0] = v.x & 0xFFFFu; o[1] = v.x >> 16; o[2] = v.y & 0xFFFFu; o[3] = v.y >> 16;
+    o[4] = v.z & 0xFFFFu; o[5] = v.z >> 16; o[6] = v.w & 0xFFFFu; o[7] = v.w >> 16;
+  }
+};
+template <>
+struct IdxVec<uint32_t> {
+  static constexpr int N = 4;
+  uint4 v;
+  __device__ __forceinline__ void load(const void *p, size_t g) {
+    v = __ldcs(reinterpret_cast<const uint4 *>(p) + g);
+  }
+  __device__ __forceinline__ void get(uint32_t (&o)[4]) const { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+
+// Per warp, two phases: (1) every lane tests its idx words against the per-node targets and
+// appends the matches to the warp's queue in shared memory (a warp scan assigns the places,
+// no atomics, no block barrier); (2) once a batch has built up the warp drains it with every
+// lane busy.  Matches are a few percent of the points, so without the queue nearly every
+// warp would run the expensive branch for one or two lanes at a time.  The scan itself is a
+// pure stream of 16-byte idx loads, two in flight per lane.
 template <int WIN, class IDX>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PPL = IdxVec<IDX>::N;
   const uint32_t nslots = a.nslots;
-  uint32_t *q_all = reinterpret_cast<uint32_t *>(smem_raw);           // [warps][REFINE_QCAP][2]
+  uint32_t *q_all = reinterpret_cast<uint32_t *>(smem_raw);           // [warps][REFINE_QCAP]
   uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw + REFINE_QBYTES);
   uint32_t *s_hi = s_lo + nslots;
   uint32_t *s_min = s_hi + nslots;
@@ -812,19 +932,20 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
   const uint32_t lo_base = smem_addr(s_lo);
   const uint32_t hi_off = nslots * 4, min_off = nslots * 8;
   const size_t n = a.n;
-  const size_t ngroups = (n + 3) / 4;
+  const size_t ngroups = (n + PPL - 1) / PPL;  // the idx buffer is padded past n (engine.cu)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t g_first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
-  uint2 *q = reinterpret_cast<uint2 *>(q_all) + (threadIdx.x >> 5) * REFINE_QCAP;  // {iteration*4 + j of lane.., node}
+  uint32_t *q = q_all + (threadIdx.x >> 5) * REFINE_QCAP;  // (iteration << 8) | (lane << 3) | j
   uint32_t cnt = 0;  // warp-uniform
+  const IDX *idx = static_cast<const IDX *>(a.idx);
 
   auto drain = [&]() {
     for (uint32_t e = lane; e < cnt; e += 32) {
-      const uint2 en = q[e];  // x: (iteration << 7) | (lane << 2) | j, y: node
-      const size_t i = (g_first - lane + (size_t)(en.x >> 7) * stride + ((en.x >> 2) & 31)) * 4 + (en.x & 3);
+      const uint32_t en = q[e];
+      const size_t i = (g_first - lane + (size_t)(en >> 8) * stride + ((en >> 3) & 31)) * PPL + (en & 7);
       if (i >= n) continue;
-      const uint32_t p = en.y;
+      const uint32_t p = ((uint32_t)idx[i] >> k0) & (nodes - 1);
       const float x = __ldg(a.x + i);
       const float4 r = __ldg(&a.rtable[p]);
       const bool in = !(x < r.x) && (x < r.y || (r.z != 0.f && x <= r.y));
@@ -837,32 +958,31 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
       uint32_t bin = __float_as_uint(tf) & 0x7FFFFFu;
       if (!(fabsf(fr - 0.5f) < f.y)) bin = descend_exact(x, r.x, r.y, k);
       accumulate_smem<WIN>(lo_base + ((rank << k) + bin) * 4, hi_off, min_off, load_w1<WIN>(a.w, i, 1.0),
-                           f2key(x));
+                           f2key(x), a.one);
     }
     __syncwarp();
     cnt = 0;
   };
 
-  Idx4<IDX> cur, nxt;
-  if (g_first < ngroups) cur.load(a.idx, g_first * 4);
+  IdxVec<IDX> cur, nxt;
+  if (g_first < ngroups) cur.load(a.idx, g_first);
   // every lane of a warp runs the same number of iterations (the warp's first lane decides)
   const size_t g_warp = g_first - lane;
   uint32_t it = 0;
   for (size_t gw = g_warp; gw < ngroups; gw += stride, ++it) {
     const size_t g = gw + lane;
-    if (g + stride < ngroups) nxt.load(a.idx, (g + stride) * 4);
-    uint32_t mm = 0;  // which of the four points match
-    uint32_t pn[4] = {0, 0, 0, 0};
+    if (g + stride < ngroups) nxt.load(a.idx, g + stride);
+    uint32_t mm = 0;  // which of the lane's points match
     if (g < ngroups) {
-      uint32_t v[4];
+      uint32_t v[PPL];
       cur.get(v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pn[j] = (v[j] >> k0) & (nodes - 1);  // masked: the padding past n holds anything
+      for (int j = 0; j < PPL; ++j) {
+        const uint32_t pn = (v[j] >> k0) & (nodes - 1);  // masked: the padding past n holds anything
         uint32_t tg;
-        if (rts) tg = s_tg[pn[j]];
+        if (rts) tg = s_tg[pn];
         else {
-          const uint2 rt = __ldg(&a.node_rt[pn[j]]);
+          const uint2 rt = __ldg(&a.node_rt[pn]);
           tg = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
         }
         if (v[j] == tg) mm |= 1u << j;
@@ -878,8 +998,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
       }
       uint32_t e = cnt + incl - c;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (mm & (1u << j)) q[e++] = make_uint2((it << 7) | (lane << 2) | j, pn[j]);
+      for (int j = 0; j < PPL; ++j)
+        if (mm & (1u << j)) q[e++] = (it << 8) | (lane << 3) | j;
       cnt += __shfl_sync(0xffffffffu, incl, 31);
       __syncwarp();
       if (cnt >= REFINE_BATCH) drain();
@@ -1097,7 +1217,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   long long weight_left = 0;
   bool left_alive = false, right_alive = false;
   // split-bin word handed to the next level: first dense-pass bin on the right of the cut
-  uint32_t sbword = a.first ? 0u : (ns.sb | SB_REFINED);  // bin part; the node prefix is added below
+  uint32_t sbword = a.first ? 0u : ns.sb;  // bin part; the node prefix is added below
+  bool sb_refined = !a.first;
   uint32_t t = 1;
   for (int depth = 0; depth < k; ++depth) {
     const float st = midpoint_f32(lo, hi);  // :472
@@ -1118,6 +1239,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
         left_alive = true;
         right_alive = false;
         sbword = 1u << a.k0;  // every bin is on the left
+        sb_refined = false;
         break;
       }
       hi = st;
@@ -1171,7 +1293,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   {
     float inv, hme;
     fast_bin_params(ns.box_lo[next_axis], ns.box_hi[next_axis], a.k_next, inv, hme);
-    a.table_next[p] = make_float4(ns.box_lo[next_axis], inv, hme, __uint_as_float(sbword + (p << a.k0)));
+    a.table_next[p] = make_float4(ns.box_lo[next_axis], inv, hme, __uint_as_float(split_word(sbword + (p << a.k0), sb_refined)));
     a.table_next_hi[p] = ns.box_hi[next_axis];
     a.table_next_split[p] = split_pos;
   }

@@ -69,6 +69,8 @@ def lib():
         _lib.oracle_imbalance.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                           C.c_int]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_set_num_threads.restype = None
+        _lib.oracle_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -214,3 +216,8 @@ def imbalance(num_parts, partition, weights):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the next oracle calls (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().oracle_set_num_threads(int(n))

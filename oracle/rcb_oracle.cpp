@@ -698,4 +698,13 @@ int oracle_num_threads(void) {
 #endif
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the timed baseline asks for the host's cores.
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 }  // extern "C"
