@@ -4,5 +4,6 @@ trait).  See DESIGN.md."""
 from .api import (BackendError, Context, Error, InputLenMismatch, Rcb, Rib,  # noqa: F401
                   default_context)
 from . import _lib  # noqa: F401
+from . import tools  # noqa: F401
 
-__all__ = ["Rcb", "Rib", "Context", "Error", "InputLenMismatch", "BackendError", "default_context"]
+__all__ = ["Rcb", "Rib", "Context", "Error", "InputLenMismatch", "BackendError", "default_context", "tools"]

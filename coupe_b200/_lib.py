@@ -19,11 +19,19 @@ COUPE_INT, COUPE_INT64, COUPE_DOUBLE = 0, 1, 2
 # every symbol the two public headers declare
 COUPE_H_SYMBOLS = ["coupe_strerror", "coupe_data_free", "coupe_data_array", "coupe_data_constant",
                    "coupe_data_fn", "coupe_rcb", "coupe_rib"]
-COUPE_B200_H_SYMBOLS = ["coupe_b200_ctx_create", "coupe_b200_ctx_destroy", "coupe_b200_nccl_unique_id",
+COUPE_B200_H_SYMBOLS = ["coupe_b200_ctx_create", "coupe_b200_ctx_destroy", "coupe_b200_ctx_device",
+                        "coupe_b200_nccl_unique_id",
                         "coupe_b200_ctx_init_comm", "coupe_b200_rcb_device", "coupe_b200_rib_device",
                         "coupe_b200_rcb_host", "coupe_b200_rib_host", "coupe_b200_host_release",
                         "coupe_b200_last_stats", "coupe_b200_last_trace", "coupe_b200_reserve",
                         "coupe_b200_set_option", "coupe_b200_version"]
+# include/coupe_b200_tools.h
+COUPE_B200_TOOLS_H_SYMBOLS = ["coupe_b200_barycentres_device", "coupe_b200_weight_linear_device",
+                              "coupe_b200_linear_alpha", "coupe_b200_weight_spike_device",
+                              "coupe_b200_weight_constant_device", "coupe_b200_weight_to_i64_device",
+                              "coupe_b200_imbalance_device", "coupe_b200_mewe_write", "coupe_b200_mewe_read",
+                              "coupe_b200_mepe_write", "coupe_b200_mepe_read", "coupe_b200_free",
+                              "coupe_b200_parse_rcb_spec"]
 
 
 class Stats(C.Structure):
@@ -104,6 +112,42 @@ def lib():
     L.coupe_b200_set_option.restype = C.c_int
     L.coupe_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.coupe_b200_version.restype = C.c_char_p
+    L.coupe_b200_ctx_device.restype = C.c_int
+    L.coupe_b200_ctx_device.argtypes = [C.c_void_p]
+    # include/coupe_b200_tools.h
+    L.coupe_b200_barycentres_device.restype = C.c_int
+    L.coupe_b200_barycentres_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.coupe_b200_weight_linear_device.restype = C.c_int
+    L.coupe_b200_weight_linear_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                  C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                                  C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double)]
+    L.coupe_b200_linear_alpha.restype = C.c_double
+    L.coupe_b200_linear_alpha.argtypes = [C.c_double] * 4
+    L.coupe_b200_weight_spike_device.restype = C.c_int
+    L.coupe_b200_weight_spike_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                 C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.coupe_b200_weight_constant_device.restype = C.c_int
+    L.coupe_b200_weight_constant_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
+    L.coupe_b200_weight_to_i64_device.restype = C.c_int
+    L.coupe_b200_weight_to_i64_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.coupe_b200_imbalance_device.restype = C.c_int
+    L.coupe_b200_imbalance_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                              C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    L.coupe_b200_mewe_write.restype = C.c_int
+    L.coupe_b200_mewe_write.argtypes = [C.c_char_p, C.c_int, C.c_uint16, C.c_uint64, C.c_void_p]
+    L.coupe_b200_mewe_read.restype = C.c_int
+    L.coupe_b200_mewe_read.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint16),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    L.coupe_b200_mepe_write.restype = C.c_int
+    L.coupe_b200_mepe_write.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
+    L.coupe_b200_mepe_read.restype = C.c_int
+    L.coupe_b200_mepe_read.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    L.coupe_b200_free.restype = None
+    L.coupe_b200_free.argtypes = [C.c_void_p]
+    L.coupe_b200_parse_rcb_spec.restype = C.c_int
+    L.coupe_b200_parse_rcb_spec.argtypes = [C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
     _lib = L
     return L
 

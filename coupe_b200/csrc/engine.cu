@@ -904,6 +904,8 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   return COUPE_ERR_OK;
 }
 
+int coupe_b200_ctx_device(const coupe_b200_ctx *c) { return c ? c->device : -1; }
+
 const char *coupe_b200_version(void) { return "coupe_b200 0.1 (sm_100a, CUDA " __DATE__ ")"; }
 
 }  // extern "C"

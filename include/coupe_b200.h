@@ -52,6 +52,8 @@ typedef struct coupe_b200_stats {
  * coupe_err value. */
 int coupe_b200_ctx_create(coupe_b200_ctx **out, int device);
 void coupe_b200_ctx_destroy(coupe_b200_ctx *ctx);
+/* CUDA ordinal the context was created on (-1 for NULL). */
+int coupe_b200_ctx_device(const coupe_b200_ctx *ctx);
 
 /* Multi-GPU: rank 0 calls coupe_b200_nccl_unique_id (128 bytes out), the host
  * framework broadcasts the bytes (torch.distributed), every rank then calls

@@ -35,9 +35,8 @@ class _Trace(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (g++)."""
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(
-        os.path.join(_HERE, "rcb_oracle.cpp")
-    ):
+    srcs = [os.path.join(_HERE, f) for f in ("rcb_oracle.cpp", "tools_oracle.cpp")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-C", _HERE, "clean", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -68,6 +67,19 @@ def lib():
         _lib.oracle_imbalance.restype = C.c_double
         _lib.oracle_imbalance.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                           C.c_int]
+        _lib.oracle_barycentres.restype = C.c_int
+        _lib.oracle_barycentres.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p]
+        _lib.oracle_weight_linear.restype = C.c_int
+        _lib.oracle_weight_linear.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                              C.c_void_p, C.c_void_p]
+        _lib.oracle_weight_spike.restype = None
+        _lib.oracle_weight_spike.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+        _lib.oracle_f64_to_i64.restype = None
+        _lib.oracle_f64_to_i64.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
+        _lib.oracle_part_loads.restype = C.c_int
+        _lib.oracle_part_loads.argtypes = [C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
         _lib.oracle_num_threads.restype = C.c_int
         _lib.oracle_set_num_threads.restype = None
         _lib.oracle_set_num_threads.argtypes = [C.c_int]
@@ -221,3 +233,57 @@ def num_threads():
 def set_num_threads(n: int) -> None:
     """OpenMP threads of the next oracle calls (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
     lib().oracle_set_num_threads(int(n))
+
+
+# ---- tool-chain steps either side of RCB (oracle/tools_oracle.cpp) ----------------------------
+def barycentres(elem_nodes, coords):
+    """elem_nodes (n_elems, nodes_per_elem) uint64, coords (n_nodes, D) f64 -> (n_elems, D) f64."""
+    en = np.ascontiguousarray(elem_nodes, dtype=np.uint64)
+    co = np.ascontiguousarray(coords, dtype=np.float64)
+    out = np.zeros((en.shape[0], co.shape[1]), dtype=np.float64)
+    err = lib().oracle_barycentres(co.shape[1], en.shape[0], en.shape[1], en.ctypes.data, co.ctypes.data,
+                                   co.shape[0], out.ctypes.data)
+    if err:
+        raise IndexError("node index out of range")
+    return out
+
+
+def weight_linear(points, axis, lo, hi):
+    """weight-gen "linear,AXIS,FROM,TO": returns (weights, (min, max, alpha))."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.zeros(pts.shape[0], dtype=np.float64)
+    mma = np.zeros(3, dtype=np.float64)
+    err = lib().oracle_weight_linear(pts.shape[1], pts.shape[0], pts.ctypes.data, int(axis), float(lo),
+                                     float(hi), out.ctypes.data, mma.ctypes.data)
+    if err:
+        raise ValueError("no points")
+    return out, tuple(mma)
+
+
+def weight_spike(points, heights, positions):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    h = np.ascontiguousarray(heights, dtype=np.float64).reshape(-1)
+    pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(h.shape[0], pts.shape[1])
+    out = np.zeros(pts.shape[0], dtype=np.float64)
+    lib().oracle_weight_spike(pts.shape[1], pts.shape[0], pts.ctypes.data, h.shape[0], h.ctypes.data,
+                              pos.ctypes.data, out.ctypes.data)
+    return out
+
+
+def f64_to_i64(values):
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.zeros(v.shape[0], dtype=np.int64)
+    lib().oracle_f64_to_i64(v.shape[0], v.ctypes.data, out.ctypes.data)
+    return out
+
+
+def part_loads(num_parts, partition, weights):
+    part = np.ascontiguousarray(partition, dtype=np.uint64)
+    w = np.ascontiguousarray(weights)
+    wtype = _wtype_of(w)
+    loads = np.zeros(num_parts, dtype=np.float64 if wtype == W_F64 else np.int64)
+    err = lib().oracle_part_loads(part.shape[0], part.ctypes.data, int(num_parts), wtype, w.ctypes.data,
+                                  loads.ctypes.data)
+    if err:
+        raise IndexError("part id out of range")
+    return loads

@@ -15,3 +15,4 @@ for name, fn in (("zero_ 2GB (write only)", lambda: t.zero_()), ("sum 2GB (read 
     e0.record(); [fn() for _ in range(5)]; e1.record(); torch.cuda.synchronize()
     print(name, 2e9 * 5 / e0.elapsed_time(e1) / 1e6, "GB/s")
 PY
+timeout 600 python tools/bench_tools.py > gpurun_out/bench_tools.json 2> gpurun_out/bench_tools.err; cat gpurun_out/bench_tools.json; tail -3 gpurun_out/bench_tools.err
