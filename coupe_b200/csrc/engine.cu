@@ -566,22 +566,21 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   };
   // walk + rank of one pass; returns the sequence number of its flag
   auto enqueue_walk = [&](int level, int k, int k0, int first, uint32_t rank_limit, const uint32_t *guard) {
-    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
-                tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
-                plan_first(c, level + 1).k};
-    const size_t bytes = ((size_t)2 << k) * 12;
-    const uint32_t nodes = 1u << level;
-    if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
-    else if (wtype == WT_I64) walk_kernel<WT_I64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
-    else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
     bool rts_;
     size_t rtb_;
     const uint64_t s = seq++;
     c->h_flags[flag_slot(s)] = 0;
-    rank_unresolved_kernel<<<1, 1024, 0, st>>>(target, nodes, node_rt, rtable, rfast,
-                                               refine_cap(level, rts_, rtb_), c->kmax_refine, gp, guard,
-                                               c->d_flags + flag_slot(s));
-    R.launched(2);
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
+                tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
+                plan_first(c, level + 1).k, rfast, refine_cap(level, rts_, rtb_), c->kmax_refine,
+                c->d_flags + flag_slot(s)};
+    const size_t bytes = ((size_t)2 << k) * 12;
+    const uint32_t nodes = 1u << level;
+    // the last block to finish ranks the undecided nodes and reports to the host flag
+    if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    else if (wtype == WT_I64) walk_kernel<WT_I64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    R.launched(1);
     return s;
   };
   // the dense first pass of `level`; kprev = bins of the level before

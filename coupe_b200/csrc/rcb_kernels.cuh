@@ -56,6 +56,7 @@ struct GlobalParams {
   uint32_t unresolved;             // nodes whose bisection needs another pass
   uint32_t w_wide;                 // some i64 weight does not fit the narrowed i32 column
   uint32_t leaf_min;               // smallest non-empty leaf path
+  uint32_t walk_ticket;            // blocks of the current walk launch that are done (reset by the last one)
   int shift;
 };
 
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   float *s_split = reinterpret_cast<float *>(s_table + (TSM ? nparents : 0));
   float *s_thi = s_split + (TSM ? nparents : 0);
   if (SMEM) {
-    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i + 1 <= nwords; i += blockDim.x) {  // (i < nwords; written so for nwords == 0)
       s_lo[i] = 0;
       s_hi[i] = 0;
       s_min[i] = (uint32_t)SKEY_EMPTY;
@@ -940,6 +941,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
   uint32_t cnt = 0;  // warp-uniform
   const IDX *idx = static_cast<const IDX *>(a.idx);
 
+  // (Measured: a wider drain with four entries per lane in flight is slower, 225 us against 185 us
+  // per pass on the C4 shard — the pass is bound by the 32-byte sectors its gathers touch.)
   auto drain = [&]() {
     for (uint32_t e = lane; e < cnt; e += 32) {
       const uint32_t en = q[e];
@@ -1029,27 +1032,21 @@ constexpr unsigned long long FLAG_VALID = 1ull << 63, FLAG_ABORTED = 1ull << 62;
 
 // Ranks the undecided nodes of a level in node order (identical on every GPU),
 // counts them and prepares their fast binning parameters: node_rt[p] =
-// {target idx, rank}, rfast[p] = {2^kr / width, 0.5 - eps}.
-__global__ void __launch_bounds__(1024)
-rank_unresolved_kernel(const uint32_t *__restrict__ target, uint32_t nodes, uint2 *__restrict__ node_rt,
-                       const float4 *__restrict__ rtable, float2 *__restrict__ rfast, uint32_t cap,
-                       int kmax, GlobalParams *gp, const uint32_t *guard,
-                       volatile unsigned long long *host_flag) {
+// {target idx, rank}, rfast[p] = {2^kr / width, 0.5 - eps}.  Run by the LAST block of the
+// walk kernel to finish (a ticket counter in GlobalParams), so a pass ends without
+// another launch; `target` / `rtable` were written by other blocks of the same launch and
+// are read past L1 (__ldcg).
+__device__ void rank_unresolved_block(const uint32_t *target, uint32_t nodes, uint2 *node_rt,
+                                      const float4 *rtable, float2 *rfast, uint32_t cap, int kmax,
+                                      GlobalParams *gp, volatile unsigned long long *host_flag) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_base;
-  if (guard && *guard != 0) {  // the whole pass was launched optimistically and did not run
-    if (threadIdx.x == 0) {
-      *host_flag = FLAG_ABORTED;
-      __threadfence_system();
-    }
-    return;
-  }
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t b = 0; b < nodes; b += blockDim.x) {
     const uint32_t p = b + threadIdx.x;
-    const uint32_t tg = p < nodes ? target[p] : TARGET_NONE;
+    const uint32_t tg = p < nodes ? __ldcg(target + p) : TARGET_NONE;
     const bool un = tg != TARGET_NONE;
     const uint32_t bal = __ballot_sync(0xffffffffu, un);
     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -1068,8 +1065,8 @@ rank_unresolved_kernel(const uint32_t *__restrict__ target, uint32_t nodes, uint
   const uint32_t unresolved = s_base;
   const int kr = refine_bits(unresolved, cap, kmax);
   for (uint32_t p = threadIdx.x; p < nodes; p += blockDim.x) {
-    if (target[p] == TARGET_NONE) continue;
-    const float4 r = rtable[p];
+    if (__ldcg(target + p) == TARGET_NONE) continue;
+    const float4 r = __ldcg(rtable + p);
     float inv, hme;
     fast_bin_params(r.x, r.y, kr, inv, hme);
     rfast[p] = make_float2(inv, hme);
@@ -1136,12 +1133,14 @@ struct WalkArgs {
   uint32_t rank_limit;       // refinement: nodes ranked at or above were not swept this pass
   const uint32_t *guard;     // optimistic launch: return at once if *guard != 0
   int k_next;                // bins of the next level's dense pass
+  float2 *rfast;             // per node: fast binning parameters of the next refinement pass
+  uint32_t refine_cap;       // histogram slots a refinement pass may use at this level
+  int kmax_refine;
+  volatile unsigned long long *host_flag;  // mapped host word the pass reports to
 };
 
 template <int WT>
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (a.guard && *a.guard != 0) return;
+__device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
   const int k = a.k;
   const uint32_t nb = 1u << k;
   unsigned long long *wtree = reinterpret_cast<unsigned long long *>(smem_raw);  // heap, 2nb
@@ -1334,6 +1333,31 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     if (left_alive) atomicMin(&a.gp->leaf_min, 2 * p);
     if (right_alive) atomicMin(&a.gp->leaf_min, 2 * p + 1);
   }
+}
+
+template <int WT>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_last;
+  if (a.guard && *a.guard != 0) {  // the whole pass was launched optimistically and does not run
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *a.host_flag = FLAG_ABORTED;
+      __threadfence_system();
+    }
+    return;
+  }
+  walk_node<WT>(a, smem_raw);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&a.gp->walk_ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) a.gp->walk_ticket = 0;
+  __threadfence();
+  rank_unresolved_block(a.target, 1u << a.level, const_cast<uint2 *>(a.node_rt), a.rtable, a.rfast,
+                        a.refine_cap, a.kmax_refine, a.gp, a.host_flag);
 }
 
 // ---------------------------------------------------------------------------

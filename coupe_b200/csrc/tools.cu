@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(256)
 f64_to_i64_kernel(size_t n, const double *__restrict__ in, long long *__restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    __stcs(out + i, __double2ll_rz(__ldcs(in + i)));  // `as i64`: toward zero, saturating, NaN -> 0
+  {  // `as i64`: toward zero, saturating, NaN -> 0 (the conversion instruction gives i64::MIN for NaN)
+    const double v = __ldcs(in + i);
+    __stcs(out + i, v != v ? 0ll : __double2ll_rz(v));
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -209,6 +212,19 @@ maxabs_kernel(size_t n, const double *__restrict__ w, unsigned long long *out_bi
 constexpr int LOADS_THREADS = 512;
 constexpr uint32_t LOADS_SMEM_PARTS = 16384;  // 128 KB of {low, high} words
 
+template <int WT>
+__device__ __forceinline__ long long load_weight_fixed(const void *__restrict__ w, size_t i, double scale) {
+  // __ldg: a thread reads 8 consecutive elements one by one; L1 keeps the line between them
+  if (WT == COUPE_B200_W_I32) return __ldg(static_cast<const int *>(w) + i);
+  if (WT == COUPE_B200_W_I64) return __ldg(static_cast<const long long *>(w) + i);
+  return __double2ll_rn(__dmul_rn(__ldg(static_cast<const double *>(w) + i), scale));
+}
+
+// Every thread walks a run of LOADS_RUN consecutive points and adds a run of equal part ids
+// once: mesh-ordered inputs (neighbours share a part) would otherwise send a whole warp to
+// one shared-memory word.
+constexpr int LOADS_RUN = 8;
+
 template <int WT, bool SMEM>
 __global__ void __launch_bounds__(LOADS_THREADS)
 part_loads_kernel(size_t n, const unsigned long long *__restrict__ part, const void *__restrict__ w,
@@ -220,25 +236,42 @@ part_loads_kernel(size_t n, const unsigned long long *__restrict__ part, const v
     __syncthreads();
   }
   bool ok = true;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const unsigned long long p = __ldcs(part + i);
-    long long v;
-    if (WT == COUPE_B200_W_I32) v = __ldcs(static_cast<const int *>(w) + i);
-    else if (WT == COUPE_B200_W_I64) v = __ldcs(static_cast<const long long *>(w) + i);
-    else v = __double2ll_rn(__dmul_rn(__ldcs(static_cast<const double *>(w) + i), scale));
+  auto add = [&](unsigned long long p, long long v) {
     if (p >= num_parts) {
       ok = false;
-      continue;
+      return;
     }
     if (SMEM) {
       const uint32_t lo = (uint32_t)v;
       const uint32_t old = atomicAdd(&s_words[p], lo);
-      uint32_t hinc = (uint32_t)(v >> 32) + (old > ~lo ? one : 0u);
+      const uint32_t hinc = (uint32_t)(v >> 32) + (old > ~lo ? one : 0u);
       if (hinc) atomicAdd(&s_words[num_parts + p], hinc);
     } else {
       atomicAdd(&loads[p], (unsigned long long)v);
     }
+  };
+  const size_t nruns = (n + LOADS_RUN - 1) / LOADS_RUN;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += stride) {
+    const size_t i0 = r * LOADS_RUN;
+    unsigned long long cur = 0;
+    long long acc = 0;
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < LOADS_RUN; ++j) {
+      if (i0 + j >= n) break;
+      const unsigned long long p = __ldg(part + i0 + j);
+      const long long v = load_weight_fixed<WT>(w, i0 + j, scale);
+      if (have && p == cur) {
+        acc = (long long)((unsigned long long)acc + (unsigned long long)v);
+      } else {
+        if (have) add(cur, acc);
+        cur = p;
+        acc = v;
+        have = true;
+      }
+    }
+    if (have) add(cur, acc);
   }
   if (!ok) atomicExch(bad, 1u);
   if (SMEM) {
@@ -434,7 +467,7 @@ int coupe_b200_imbalance_device(coupe_b200_ctx *ctx, void *stream, uintptr_t n, 
     if (n > 0) {
       const bool smem = num_parts <= LOADS_SMEM_PARTS;
       const size_t bytes = smem ? (size_t)num_parts * 8 : 0;
-      const int grid = grid_for(device, n, LOADS_THREADS, 1);
+      const int grid = grid_for(device, (n + LOADS_RUN - 1) / LOADS_RUN, LOADS_THREADS, 1);
       const unsigned long long *pd = reinterpret_cast<const unsigned long long *>(part_dev);
 #define LAUNCH(WT)                                                                                           \
   do {                                                                                                       \
