@@ -41,6 +41,7 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   bool load() {
     if (handle) return true;
     // Resolve against the NCCL already mapped into the process (torch's) when there is one.
@@ -53,6 +54,7 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
     CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
     return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
   }
 };
@@ -201,6 +203,11 @@ struct coupe_b200_ctx {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange of the level histograms (rcb_kernels.cuh: Xchg); off -> NCCL all-reduces
+  bool xchg_ok = false;
+  int use_xchg_opt = 1;
+  unsigned char *xchg_peer[XCHG_MAX_WORLD] = {nullptr};  // [rank] is this rank's own cudaMalloc'ed buffer
+  unsigned int *xchg_aux = nullptr;                       // {ticket, error}
   // options
   int kmax_a = 8, nb_smem_log2 = 14, kmax_refine = 10, force_global = 0, trace_on = 1, time_sweeps = 0;
   std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
@@ -212,6 +219,8 @@ struct coupe_b200_ctx {
 };
 
 namespace {
+
+void setup_xchg(coupe_b200_ctx *c);
 
 size_t sweep_smem_bytes(int level, bool table_in_smem) {
   // the three histogram arrays sit at fixed offsets (rcb_kernels.cuh: HIST_BYTES), the table after them
@@ -531,6 +540,27 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     idx16 = idx16 && pl.smem && level + pl.k <= 16;
   }
   float2 *rfast = c->rfast.as<float2>();
+  // multi-GPU: histograms travel through the peer-memory exchange when every pass of the call fits
+  // its slots (shared-memory mode at every level), else through NCCL all-reduces
+  bool use_xchg = c->world > 1 && c->xchg_ok && c->use_xchg_opt;
+  for (int level = 0; level < L; ++level) use_xchg = use_xchg && plan_first(c, level).smem;
+  auto make_xchg = [&](uint64_t pass_seq) {
+    Xchg x{};
+    if (!use_xchg) return x;
+    for (int r = 0; r < c->world; ++r) x.peer[r] = c->xchg_peer[r];
+    x.world = c->world;
+    x.rank = c->rank;
+    x.slot = (uint32_t)(pass_seq % XCHG_DEPTH);
+    x.seq = pass_seq + 1;
+    x.ticket = c->xchg_aux;
+    x.error = c->xchg_aux + 1;
+    return x;
+  };
+  auto allreduce_hist = [&](uint32_t count) {
+    if (use_xchg) return;  // pushed by reduce_partials_kernel, gathered by walk_kernel
+    R.allreduce(hist_w, count, ncclUint64, ncclSum);
+    R.allreduce(hist_min, count, ncclUint32, ncclMin);
+  };
   // histogram slots a refinement pass may use at a level (shared memory next to the match queue
   // and, when it fits, the per-node target table)
   auto refine_cap = [&](int level, bool &rts, size_t &rt_bytes) {
@@ -573,7 +603,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
                 tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
                 plan_first(c, level + 1).k, rfast, refine_cap(level, rts_, rtb_), c->kmax_refine,
-                c->d_flags + flag_slot(s)};
+                c->d_flags + flag_slot(s), make_xchg(s)};
     const size_t bytes = ((size_t)2 << k) * 12;
     const uint32_t nodes = 1u << level;
     // the last block to finish ranks the undecided nodes and reports to the host flag
@@ -622,11 +652,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     S.dense_sweeps += 1;
     if (plan.smem) {
       reduce_partials_kernel<<<(nb + 31) / 32, 256, 0, st>>>(sa.part_w, sa.part_min, sweep_grid, nb,
-                                                             hist_w, hist_min, guard);
+                                                             hist_w, hist_min, guard, make_xchg(seq));
       R.launched();
     }
-    R.allreduce(hist_w, nb, ncclUint64, ncclSum);
-    R.allreduce(hist_min, nb, ncclUint32, ncclMin);
+    allreduce_hist(nb);
     return enqueue_walk(level, k, k, 1, 0, guard);
   };
   auto enqueue_refine_round = [&](int level, int k0, uint32_t unresolved) {
@@ -649,11 +678,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     }
     time_end();
     reduce_partials_kernel<<<(nslots + 31) / 32, 256, 0, st>>>(ra.part_w, ra.part_min, sweep_grid,
-                                                               nslots, hist_w, hist_min, nullptr);
+                                                               nslots, hist_w, hist_min, nullptr, make_xchg(seq));
     R.launched(2);
     S.refine_sweeps += 1;
-    R.allreduce(hist_w, nslots, ncclUint64, ncclSum);
-    R.allreduce(hist_min, nslots, ncclUint32, ncclMin);
+    allreduce_hist(nslots);
     return enqueue_walk(level, kr, k0, 0, limit, nullptr);
   };
   auto advance_level = [&]() {
@@ -724,8 +752,14 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   }
   c->flag_seq = seq;
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
+  if (use_xchg) CU(cudaMemcpyAsync(c->h_pinned + 1, c->xchg_aux + 1, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
   memcpy(&S.weight_shift, c->h_pinned, 4);
+  S.peer_exchange = use_xchg ? 1 : 0;
+  if (use_xchg && c->h_pinned[1] != 0) {
+    fprintf(stderr, "coupe_b200: a rank did not deliver its histogram in time (peer-memory exchange)\n");
+    return COUPE_ERR_CRASH;
+  }
   for (size_t e = 0; e + 1 < ev_used; e += 2) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->events[e], c->events[e + 1]));
@@ -756,6 +790,88 @@ int guarded(coupe_b200_ctx *c, bool rib, void *stream, uint64_t *part_dev, uintp
   } catch (...) {
     return COUPE_ERR_CRASH;
   }
+}
+
+// Peer-memory exchange: allocate this rank's buffer, share its IPC handle with the other ranks
+// of the box (all-gather through the NCCL communicator) and map theirs.  Any failure (ranks on
+// different nodes, IPC disabled in a container, no peer access) leaves xchg_ok false.
+void setup_xchg(coupe_b200_ctx *c) {
+  c->xchg_ok = false;
+  if (c->world < 2 || c->world > XCHG_MAX_WORLD || !g_nccl.AllGather) return;
+  if (const char *e = getenv("COUPE_B200_NO_PEER_EXCHANGE"))
+    if (*e && *e != '0') return;
+  void *mine = nullptr, *hbuf = nullptr;
+  unsigned int *aux = nullptr;
+  int ok = 1;
+  const size_t bytes = xchg_bytes(c->world);
+  if (cudaMalloc(&mine, bytes) != cudaSuccess || cudaMemset(mine, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && (cudaMalloc(reinterpret_cast<void **>(&aux), 64) != cudaSuccess || cudaMemset(aux, 0, 64) != cudaSuccess)) ok = 0;
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  if (ok && cudaIpcGetMemHandle(&h, mine) != cudaSuccess) ok = 0;
+  // every rank takes part in the two collectives below whatever happened above
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  const size_t rec = 64 + 8;  // handle + "ok" word
+  std::vector<unsigned char> all((size_t)c->world * rec);
+  bool coll_ok = cudaMalloc(&hbuf, (size_t)(c->world + 1) * rec) == cudaSuccess;
+  if (coll_ok) {
+    unsigned char send[72];
+    memcpy(send, &h, 64);
+    const unsigned long long okw = (unsigned long long)ok;
+    memcpy(send + 64, &okw, 8);
+    unsigned char *d = static_cast<unsigned char *>(hbuf);
+    coll_ok = cudaMemcpy(d, send, rec, cudaMemcpyHostToDevice) == cudaSuccess &&
+              g_nccl.AllGather(d, d + rec, rec, ncclUint8, c->comm, nullptr) == ncclSuccess &&
+              cudaStreamSynchronize(nullptr) == cudaSuccess &&
+              cudaMemcpy(all.data(), d + rec, (size_t)c->world * rec, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  if (hbuf) cudaFree(hbuf);
+  bool every = coll_ok;
+  for (int r = 0; every && r < c->world; ++r) {
+    unsigned long long okw;
+    memcpy(&okw, all.data() + (size_t)r * rec + 64, 8);
+    every = okw == 1;
+  }
+  if (every) {
+    for (int r = 0; r < c->world && every; ++r) {
+      if (r == c->rank) {
+        c->xchg_peer[r] = static_cast<unsigned char *>(mine);
+        continue;
+      }
+      cudaIpcMemHandle_t ph;
+      memcpy(&ph, all.data() + (size_t)r * rec, 64);
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) every = false;
+      c->xchg_peer[r] = static_cast<unsigned char *>(p);
+    }
+  }
+  cudaGetLastError();
+  // all ranks must agree: one more tiny all-reduce (min of "mapped everything")
+  {
+    unsigned int *d = nullptr;
+    unsigned int v = every ? 1u : 0u;
+    if (cudaMalloc(reinterpret_cast<void **>(&d), 4) == cudaSuccess &&
+        cudaMemcpy(d, &v, 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+        g_nccl.AllReduce(d, d, 1, ncclUint32, ncclMin, c->comm, nullptr) == ncclSuccess &&
+        cudaStreamSynchronize(nullptr) == cudaSuccess && cudaMemcpy(&v, d, 4, cudaMemcpyDeviceToHost) == cudaSuccess)
+      every = every && v == 1;
+    else
+      every = false;
+    if (d) cudaFree(d);
+  }
+  if (!every) {
+    for (int r = 0; r < c->world; ++r) {
+      if (r != c->rank && c->xchg_peer[r]) cudaIpcCloseMemHandle(c->xchg_peer[r]);
+      c->xchg_peer[r] = nullptr;
+    }
+    if (mine) cudaFree(mine);
+    if (aux) cudaFree(aux);
+    cudaGetLastError();
+    if (c->rank == 0) fprintf(stderr, "coupe_b200: peer-memory exchange unavailable, using NCCL all-reduces\n");
+    return;
+  }
+  c->xchg_aux = aux;
+  c->xchg_ok = true;
 }
 
 }  // namespace
@@ -800,6 +916,15 @@ int coupe_b200_ctx_create(coupe_b200_ctx **out, int device) {
 void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->xchg_ok) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r) {
+      if (!c->xchg_peer[r]) continue;
+      if (r == c->rank) cudaFree(c->xchg_peer[r]);
+      else cudaIpcCloseMemHandle(c->xchg_peer[r]);
+    }
+    if (c->xchg_aux) cudaFree(c->xchg_aux);
+  }
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->node_rt, &c->rfast, &c->tsp_a, &c->tsp_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
                  &c->nodes_b, &c->table_a, &c->table_b, &c->thi_a, &c->thi_b, &c->rtable, &c->gp, &c->tr_visited,
@@ -835,6 +960,7 @@ int coupe_b200_ctx_init_comm(coupe_b200_ctx *c, const void *unique_id128, int ra
   if (g_nccl.CommInitRank(&c->comm, world, id, rank) != ncclSuccess) return COUPE_ERR_CRASH;
   c->rank = rank;
   c->world = world;
+  setup_xchg(c);  // optional: without it the histograms go through NCCL all-reduces
   return COUPE_ERR_OK;
 }
 
@@ -899,6 +1025,7 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "force_global") c->force_global = value != 0;
   else if (s == "trace") c->trace_on = value != 0;
   else if (s == "time_sweeps") c->time_sweeps = (int)value;
+  else if (s == "peer_exchange") c->use_xchg_opt = value != 0;
   else return COUPE_ERR_NOT_FOUND;
   return COUPE_ERR_OK;
 }

@@ -805,12 +805,46 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------
+// Multi-GPU exchange of the level histograms over peer memory (NVLink): every
+// rank owns one exchange buffer, mapped into every other rank of the box through
+// CUDA IPC.  A pass PUSHES its reduced histogram into slot [pass % 4][own rank] of
+// every rank's buffer (reduce_partials_kernel) and then raises flag [pass % 4][own
+// rank] there; the walk of the same pass waits for the flags of all ranks in its
+// OWN buffer and sums the copies in rank order.  One NVLink store round instead of
+// two NCCL all-reduces per pass; integer payloads, so the result is the same on
+// every rank.  Four slots: no two consecutive passes are both skipped by the
+// optimistic guard, so between two uses of a slot every rank has completed the
+// walk of a later pass, which implies every peer is done reading the slot.
+// ---------------------------------------------------------------------------
+constexpr uint32_t XCHG_SLOTS = 1u << 14;
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr int XCHG_DEPTH = 4;
+constexpr size_t XCHG_SRC_BYTES = (size_t)XCHG_SLOTS * 12;  // u64 sums, then u32 min keys
+__host__ __device__ inline size_t xchg_payload_off(int world, uint32_t slot, int src) {
+  return ((size_t)slot * world + src) * XCHG_SRC_BYTES;
+}
+__host__ __device__ inline size_t xchg_flag_off(int world, uint32_t slot, int src) {
+  return (size_t)XCHG_DEPTH * world * XCHG_SRC_BYTES + ((size_t)slot * XCHG_MAX_WORLD + src) * 8;
+}
+__host__ __device__ inline size_t xchg_bytes(int world) { return xchg_flag_off(world, XCHG_DEPTH, 0) + 64; }
+
+struct Xchg {
+  unsigned char *peer[XCHG_MAX_WORLD];  // every rank's exchange buffer as mapped in this process (own included)
+  int world, rank;                      // world <= 1: exchange off
+  uint32_t slot;                        // pass % XCHG_DEPTH
+  unsigned long long seq;               // pass number + 1 (flags only grow)
+  unsigned int *ticket;                 // local: blocks of the pushing kernel that are done
+  unsigned int *error;                  // local: set when a wait timed out
+};
+
 // Sum / min of the per-block partial histograms: 32 bins x 8 slices of blocks
-// per thread block, so that even a 2^8-bin level keeps the SMs busy.
+// per thread block, so that even a 2^8-bin level keeps the SMs busy.  With an
+// exchange the result goes to every rank's buffer instead of hist_w / hist_min.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__restrict__ part_min,
                        int nblocks, uint32_t nb, unsigned long long *__restrict__ hist_w,
-                       uint32_t *__restrict__ hist_min, const uint32_t *guard) {
+                       uint32_t *__restrict__ hist_min, const uint32_t *guard, const Xchg x) {
   __shared__ unsigned long long s_w[8][32];
   if (guard && *guard != 0) return;
   __shared__ uint32_t s_m[8][32];
@@ -832,8 +866,30 @@ reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__r
       acc += s_w[s][lane];
       m = min(m, s_m[s][lane]);
     }
-    hist_w[i] = acc;
-    hist_min[i] = m;
+    if (x.world > 1) {
+      const size_t off = xchg_payload_off(x.world, x.slot, x.rank);
+      for (int r = 0; r < x.world; ++r) {
+        reinterpret_cast<unsigned long long *>(x.peer[r] + off)[i] = acc;
+        reinterpret_cast<uint32_t *>(x.peer[r] + off + (size_t)XCHG_SLOTS * 8)[i] = m;
+      }
+    } else {
+      hist_w[i] = acc;
+      hist_min[i] = m;
+    }
+  }
+  if (x.world > 1) {  // the last block to finish raises this rank's flag in every buffer
+    __shared__ uint32_t s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(x.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      *x.ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < x.world; ++r)
+        *reinterpret_cast<volatile unsigned long long *>(x.peer[r] + xchg_flag_off(x.world, x.slot, x.rank)) = x.seq;
+      __threadfence_system();
+    }
   }
 }
 
@@ -1137,6 +1193,7 @@ struct WalkArgs {
   uint32_t refine_cap;       // histogram slots a refinement pass may use at this level
   int kmax_refine;
   volatile unsigned long long *host_flag;  // mapped host word the pass reports to
+  Xchg x;                    // multi-GPU: read the histogram from the exchange buffer (world > 1)
 };
 
 template <int WT>
@@ -1167,9 +1224,40 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
   }
   const unsigned long long wscale = a.w_is_const ? (unsigned long long)a.gp->wconst : 1ull;
   const size_t hbase = (size_t)(a.first ? p : a.node_rt[p].y) * nb;  // refinement histograms are ranked
-  for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-    wtree[nb + i] = a.hist_w[hbase + i] * wscale;
-    mtree[nb + i] = a.hist_min[hbase + i];
+  if (a.x.world > 1) {
+    // wait for every rank's push of this pass (flags in this rank's own buffer), then sum the copies
+    const unsigned char *own = a.x.peer[a.x.rank];
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int r = 0; r < a.x.world; ++r) {
+        const volatile unsigned long long *f =
+            reinterpret_cast<const volatile unsigned long long *>(own + xchg_flag_off(a.x.world, a.x.slot, r));
+        while (*f < a.x.seq) {
+          if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; report instead of hanging the GPU
+            *a.x.error = 1;
+            break;
+          }
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+      unsigned long long acc = 0;
+      uint32_t m = KEY_EMPTY;
+      for (int r = 0; r < a.x.world; ++r) {
+        const unsigned char *src = own + xchg_payload_off(a.x.world, a.x.slot, r);
+        acc += __ldcg(reinterpret_cast<const unsigned long long *>(src) + hbase + i);
+        m = min(m, __ldcg(reinterpret_cast<const uint32_t *>(src + (size_t)XCHG_SLOTS * 8) + hbase + i));
+      }
+      wtree[nb + i] = acc * wscale;
+      mtree[nb + i] = m;
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+      wtree[nb + i] = a.hist_w[hbase + i] * wscale;
+      mtree[nb + i] = a.hist_min[hbase + i];
+    }
   }
   __syncthreads();
   for (int d = k - 1; d >= 0; --d) {

@@ -22,7 +22,7 @@ def _worker(rank, world, port, case, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        pts, w, iters, tol, rib, empty_last = case
+        pts, w, iters, tol, rib, empty_last, peer = case
         n = pts.shape[0]
         b, e = cdist.shard_range(n, rank, world)
         if rank == world - 1 and empty_last:  # last rank holds nothing
@@ -30,12 +30,19 @@ def _worker(rank, world, port, case, out):
         elif empty_last:
             b, e = cdist.shard_range(n, rank, world - 1)
         ctx = cdist.init_comm(coupe_b200.Context(rank))
+        ctx.set_option("peer_exchange", int(peer))
         part = torch.full((e - b,), -1, dtype=torch.int64, device=dev)
         tw = torch.from_numpy(w[b:e]).to(dev) if w.ndim else w
         algo = (coupe_b200.Rib if rib else coupe_b200.Rcb)(iters, tol, ctx)
         algo.partition(part, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
         torch.cuda.synchronize()
-        out.put((rank, b, part.cpu().numpy().astype(np.uint64), ctx.stats()["collectives"]))
+        calls = 3  # several calls on one context: the exchange slots and flags are reused across calls
+        for _ in range(calls - 1):
+            again = torch.full_like(part, -1)
+            algo.partition(again, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
+            assert torch.equal(again, part)
+        st = ctx.stats()
+        out.put((rank, b, part.cpu().numpy().astype(np.uint64), st["collectives"], st["peer_exchange"]))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -57,6 +64,8 @@ def run_sharded(case, world=2):
     for p in procs:
         p.join(timeout=60)
     assert all(r[3] > 0 for r in res), "no NCCL collective was issued"
+    peer = case[-1]
+    assert all(r[4] == int(peer) for r in res), "peer-memory exchange was requested but not used (or the reverse)"
     return np.concatenate([r[2] for r in res])
 
 
@@ -66,13 +75,14 @@ def two_gpus():
         pytest.skip("needs two CUDA devices")
 
 
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-exchange", "nccl"])
 @pytest.mark.parametrize("wkind,dim,iters,tol,empty_last", [
     ("i64", 3, 10, 0.05, False),
     ("f64", 3, 9, 0.05, False),
     ("i64big", 2, 8, 0.001, False),
     ("const", 2, 7, 0.0, True),
 ])
-def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, empty_last):
+def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, empty_last, peer):
     rng = np.random.default_rng(11)
     n = 300_007
     k = rng.integers(0, 5, n)
@@ -81,7 +91,7 @@ def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, em
          "i64big": rng.integers(1, 2**40, n).astype(np.int64),
          "f64": rng.uniform(0.5, 1.5, n),
          "const": np.array(3, dtype=np.int32)}[wkind]
-    got = run_sharded((pts, w, iters, tol, False, empty_last))
+    got = run_sharded((pts, w, iters, tol, False, empty_last, peer))
     assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=1))
 
 
@@ -94,7 +104,7 @@ def test_sharded_rib_matches_single_gpu(two_gpus):
     c, s = np.cos(0.7), np.sin(0.7)
     pts = pts @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]]).T
     w = rng.integers(1, 10, n).astype(np.int64)
-    got = run_sharded((pts, w, 6, 0.05, True, False))
+    got = run_sharded((pts, w, 6, 0.05, True, False, True))
     dev = torch.device("cuda", 0)
     part = torch.empty(n, dtype=torch.int64, device=dev)
     coupe_b200.Rib(6, 0.05).partition(part, (torch.from_numpy(pts).to(dev), torch.from_numpy(w).to(dev)))
