@@ -57,7 +57,10 @@ def gen_shard(torch, n, seed, device):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons.  Started before the warm-up (nvidia-smi needs a few
+    hundred ms to deliver its first line), it keeps host timestamps; the report uses the samples that
+    fall inside the timed region and, if that region was shorter than the sampling period, the samples
+    taken under load from the warm-up on."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -65,13 +68,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.lines = []
+        self.lines = []  # (host time, line)
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -80,32 +83,48 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, load_from, t_begin, t_end):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        timed = [r for r in self.lines if t_begin <= r[0] <= t_end + 0.03]
+        window = "timed region"
+        if len(timed) < 3:
+            timed = [r for r in self.lines if load_from <= r[0] <= t_end + 0.03]
+            window = "warm-up + timed region (timed region shorter than three sampling periods)"
+        sm, mx, reasons = parse(timed)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -204,11 +223,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
+    t_load = time.time()
     for _ in range(max(args.warmup, 3)):
         algo.partition(part, (pts, w))
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches = 0
     dense_ms = 0.0
     dense_n = 0
@@ -216,6 +237,7 @@ def run_ours(args):
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         algo.partition(part, (pts, w))
@@ -226,7 +248,7 @@ def run_ours(args):
         refine_n += st["refine_sweeps"]
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load, t_begin, time.time())
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

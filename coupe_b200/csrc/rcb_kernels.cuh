@@ -852,11 +852,28 @@ reduce_partials_kernel(const long long *__restrict__ part_w, const uint32_t *__r
   const uint32_t i = blockIdx.x * 32 + lane;
   unsigned long long acc = 0;
   uint32_t m = KEY_EMPTY;
-  if (i < nb)
-    for (int b = slice; b < nblocks; b += 8) {
+  if (i < nb) {
+    // the loads of eight partial blocks in flight at a time: the kernel is a latency chain otherwise
+    int b = slice;
+    for (; b + 56 < nblocks; b += 64) {
+      unsigned long long v[8];
+      uint32_t k[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = (unsigned long long)part_w[(size_t)(b + 8 * u) * nb + i];
+        k[u] = part_min[(size_t)(b + 8 * u) * nb + i];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc += v[u];
+        m = min(m, k[u]);
+      }
+    }
+    for (; b < nblocks; b += 8) {
       acc += (unsigned long long)part_w[(size_t)b * nb + i];
       m = min(m, part_min[(size_t)b * nb + i]);
     }
+  }
   s_w[slice][lane] = acc;
   s_m[slice][lane] = m;
   __syncthreads();
