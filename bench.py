@@ -234,6 +234,7 @@ def run_ours(args):
     dense_ms = 0.0
     dense_n = 0
     refine_n = 0
+    refine_pts = 0
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -246,6 +247,7 @@ def run_ours(args):
         dense_ms += st["dense_sweep_ms"]
         dense_n += st["dense_sweeps"]
         refine_n += st["refine_sweeps"]
+        refine_pts += st["refine_points"]
     e1.record()
     barrier()
     clocks = sampler.stop(t_load, t_begin, time.time())
@@ -329,7 +331,8 @@ def run_ours(args):
         "config": {"workload": workload_name(n, world), "points_per_gpu": n, "dim": DIM,
                    "iter_count": ITERS, "tolerance": TOL, "weights": "f64 (i64 fixed-point accumulation)",
                    "l2": "inputs (4 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
-                   "refine_sweeps_per_step": refine_n / args.steps},
+                   "refine_sweeps_per_step": refine_n / args.steps,
+                   "refine_points_per_step": refine_pts / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (8 * DIM + 8),
                 "d2h_bytes_per_step": n * 8, "steps": e2e_steps,

@@ -222,11 +222,12 @@ namespace {
 
 void setup_xchg(coupe_b200_ctx *c);
 
-size_t sweep_smem_bytes(int level, bool table_in_smem) {
-  // the three histogram arrays sit at fixed offsets (rcb_kernels.cuh: HIST_BYTES), the table after them
-  size_t b = HIST_BYTES;
-  if (table_in_smem) b += ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float));
-  return b;
+// Shared memory of a dense sweep in shared-memory mode: the three histogram arrays at fixed
+// offsets (rcb_kernels.cuh: HIST_BYTES), then the per-parent table replicated 2^rep_log2 times,
+// the split positions and the bracket ends.
+size_t sweep_smem_bytes(int level, int rep_log2) {
+  const size_t parents = (size_t)1 << (level > 0 ? level - 1 : 0);
+  return HIST_BYTES + (parents << rep_log2) * sizeof(float4) + parents * 2 * sizeof(float);
 }
 
 template <int WIN, bool ROOT>
@@ -295,6 +296,7 @@ struct FirstPlan {
   bool smem;           // block-private shared-memory histograms, else L2 atomics
   int copies_log2;     // privatised copies per block (smem mode)
   bool table_in_smem;  // per-parent table staged in shared memory
+  int table_rep_log2;  // ... replicated 2^this times (bank-private copies at the deep levels)
   size_t bytes;        // dynamic shared memory
 };
 
@@ -305,12 +307,15 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
   p.table_in_smem = true;
   if (p.smem) {
     p.copies_log2 = std::min(5, c->nb_smem_log2 - (level + p.k));
-    p.bytes = sweep_smem_bytes(level, true);
+    p.table_rep_log2 = 3;
+    while (p.table_rep_log2 > 0 && sweep_smem_bytes(level, p.table_rep_log2) > c->max_smem) --p.table_rep_log2;
+    p.bytes = sweep_smem_bytes(level, p.table_rep_log2);
     if (p.bytes > c->max_smem) p.smem = false;
   }
   if (!p.smem) {
     p.k = std::max(1, std::min(c->kmax_a, 17 - level));
     p.copies_log2 = 0;
+    p.table_rep_log2 = 0;
     const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float));
     p.table_in_smem = tb <= 64 * 1024;
     p.bytes = p.table_in_smem ? tb : 0;
@@ -641,6 +646,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.copies_log2 = plan.copies_log2;
     sa.w_vec = ((uintptr_t)wp % 16) == 0;
     sa.one = 1;
+    sa.table_rep_log2 = plan.table_rep_log2;
     if (!plan.smem) {
       fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb, guard);
       R.launched();
@@ -669,7 +675,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const uint32_t nslots = limit << kr;
     const size_t rbytes = (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
     RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
-                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u};
+                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u, gp};
     time_begin(1);
     switch (win) {
       case WIN_I32: launch_refine<WIN_I32>(idx16, sweep_grid, rbytes, st, ra); break;
@@ -751,11 +757,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     pending = next_pending;
   }
   c->flag_seq = seq;
+  CU(cudaMemcpyAsync(c->h_pinned + 2, &gp->refine_points, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
   if (use_xchg) CU(cudaMemcpyAsync(c->h_pinned + 1, c->xchg_aux + 1, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
   memcpy(&S.weight_shift, c->h_pinned, 4);
   S.peer_exchange = use_xchg ? 1 : 0;
+  memcpy(&S.refine_points, c->h_pinned + 2, 8);
   if (use_xchg && c->h_pinned[1] != 0) {
     fprintf(stderr, "coupe_b200: a rank did not deliver its histogram in time (peer-memory exchange)\n");
     return COUPE_ERR_CRASH;

@@ -57,6 +57,7 @@ struct GlobalParams {
   uint32_t w_wide;                 // some i64 weight does not fit the narrowed i32 column
   uint32_t leaf_min;               // smallest non-empty leaf path
   uint32_t walk_ticket;            // blocks of the current walk launch that are done (reset by the last one)
+  unsigned long long refine_points;  // points the refinement sweeps of the call re-binned (statistics)
   int shift;
 };
 
@@ -350,6 +351,7 @@ struct SweepArgs {
   int level, k, kprev;
   int copies_log2;           // SMEM mode: 2^copies_log2 lane-private copies per block
   int w_vec;                 // weights are 16-byte aligned
+  int table_rep_log2;        // the staged per-parent table is replicated 2^this times (bank-private copies)
   uint32_t one;              // 1, from the host: a literal 1 turns `red.shared.add` into ATOMS.POPC.INC,
                              // which is several times slower than ATOMS.ADD on scattered addresses
 };
@@ -604,7 +606,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   uint32_t *s_hi = reinterpret_cast<uint32_t *>(smem_raw + HIST_HI_OFF);
   float4 *s_table = reinterpret_cast<float4 *>(smem_raw + (SMEM ? HIST_BYTES : 0));
   const int nparents = 1 << (level > 0 ? level - 1 : 0);
-  float *s_split = reinterpret_cast<float *>(s_table + (TSM ? nparents : 0));
+  // The table is read with one 16-byte load per point: at the deep levels 8 lanes of a quarter
+  // warp would hit random entries, i.e. random groups of four banks, and serialise.  It is
+  // therefore replicated 2^rlog times, copy c of entry p at index (p << rlog) + c, and lane l
+  // reads copy l % 2^rlog: with 8 copies every lane of a quarter warp owns its bank group.
+  const int rlog = TSM ? a.table_rep_log2 : 0;
+  const uint32_t rep_lane = threadIdx.x & ((1u << rlog) - 1);
+  float *s_split = reinterpret_cast<float *>(s_table + (TSM ? ((size_t)nparents << rlog) : 0));
   float *s_thi = s_split + (TSM ? nparents : 0);
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i + 1 <= nwords; i += blockDim.x) {  // (i < nwords; written so for nwords == 0)
@@ -613,12 +621,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       s_min[i] = (uint32_t)SKEY_EMPTY;
     }
   }
-  if (TSM)
+  if (TSM) {
+    for (int i = threadIdx.x; i < (nparents << rlog); i += blockDim.x) s_table[i] = a.table[i >> rlog];
     for (int i = threadIdx.x; i < nparents; i += blockDim.x) {
-      s_table[i] = a.table[i];
       s_split[i] = a.table_split[i];
       s_thi[i] = a.table_hi[i];
     }
+  }
   __syncthreads();
   const double scale = (WIN == WIN_F64) ? a.gp->scale : 1.0;
   // address of this lane's copy of slot 0; slot s sits slot_stride bytes * s further
@@ -649,7 +658,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t p = pv[j] >> kprev;
-      const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
+      const float4 e = TSM ? s_table[(p << rlog) + rep_lane] : __ldg(&a.table[p]);
       sel[j] = sel_left;
       if (!ROOT) {  // child = (2 idx + 1 >= split word); equality marks the refined bin
         const uint32_t tw = __float_as_uint(e.w), q = 2 * pv[j] + 1;
@@ -669,7 +678,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t p = pv[j] >> kprev;
-        const uint32_t tw = __float_as_uint(TSM ? s_table[p].w : __ldg(&a.table[p]).w);
+        const uint32_t tw = __float_as_uint(TSM ? s_table[(p << rlog) + rep_lane].w : __ldg(&a.table[p]).w);
         if (2 * pv[j] + 1 == tw) {
           const float split = TSM ? s_split[p] : __ldg(a.table_split + p);
           sel[j] = !(__ldg(a.xp + i0 + j) < split) ? sel_right : sel_left;
@@ -680,7 +689,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t p = pv[j] >> kprev;
-        const float4 e = TSM ? s_table[p] : __ldg(&a.table[p]);
+        const float4 e = TSM ? s_table[(p << rlog) + rep_lane] : __ldg(&a.table[p]);
         const float t = __fmul_rn(__fsub_rn(x[j], e.x), e.y);
         const float tf = __fadd_rd(t, 8388608.f);
         const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
@@ -701,30 +710,33 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     }
     if (SMEM) {
       uint32_t addr[4];
+      int mn[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) addr[j] = lo_base + slot[j] * slot_stride;
+      // the four running minima are read first, so that these loads and the four returning adds
+      // below are all in flight together (a stale minimum only lets a redundant atomic min through)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mn[j] = lds_min_of(addr[j]);
       if (WIN == WIN_CONST) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) reds_add(addr[j], a.one);  // a block sees fewer than 2^32 points
       } else if (((w[0] | w[1] | w[2] | w[3]) >> 32) == 0) {
-        // four non-negative weights below 2^32 (the common case): one returning add each, the
-        // carries out of the low words summed through the carry flag
-        uint32_t old[4], carries;
+        // four non-negative weights below 2^32 (the common case): one returning add each; the carry
+        // out of the low word goes to the high word (with 2^30-sized fixed-point weights some lane
+        // of a warp carries at nearly every step, so this is not a rare path)
+        uint32_t old[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) old[j] = atoms_add(addr[j], (uint32_t)w[j]);
-        asm("{\n\t.reg .u32 t;\n\t"
-            "add.cc.u32 t, %1, %5;\n\t addc.u32 %0, 0, 0;\n\t"
-            "add.cc.u32 t, %2, %6;\n\t addc.u32 %0, %0, 0;\n\t"
-            "add.cc.u32 t, %3, %7;\n\t addc.u32 %0, %0, 0;\n\t"
-            "add.cc.u32 t, %4, %8;\n\t addc.u32 %0, %0, 0;\n\t}"
-            : "=r"(carries)
-            : "r"(old[0]), "r"(old[1]), "r"(old[2]), "r"(old[3]), "r"((uint32_t)w[0]), "r"((uint32_t)w[1]),
-              "r"((uint32_t)w[2]), "r"((uint32_t)w[3]));
-        if (carries) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (old[j] > ~(uint32_t)w[j]) reds_add(addr[j] + HIST_HI_OFF, a.one);
-        }
+        for (int j = 0; j < 4; ++j)
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t.reg .u32 t, c;\n\t"
+              "add.cc.u32 t, %0, %1;\n\t"
+              "addc.u32 c, 0, 0;\n\t"
+              "setp.ne.u32 p, c, 0;\n\t"
+              "@p red.shared.add.u32 [%2+%3], %4;\n\t}"
+              ::"r"(old[j]), "r"((uint32_t)w[j]), "r"(addr[j]), "n"(HIST_HI_OFF), "r"(a.one)
+              : "memory");
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -735,18 +747,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
           if (hinc != 0) reds_add(addr[j] + HIST_HI_OFF, (uint32_t)hinc);
         }
       }
-      // running minimum: one plain load and compare per point; a warp takes the update branch
-      // often (some lane lowers some minimum), so the branch is four fire-and-forget mins
-      int key[4];
-      bool lower = false;
+      // only the lanes that lower a minimum (about one point in twenty) touch the atomic unit
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        key[j] = f2skey(x[j]);
-        lower = lower || key[j] < lds_min_of(addr[j]);
-      }
-      if (lower) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) reds_min_of(addr[j], key[j]);
+        const int key = f2skey(x[j]);
+        if (key < mn[j]) reds_min_of(addr[j], key);
       }
     } else {
 #pragma unroll
@@ -942,6 +947,7 @@ struct RefineArgs {
   int level, k, k0;        // k0: bins of the dense pass (idx = (node << k0) + bin)
   int rt_in_smem;
   uint32_t one;            // 1, from the host (see SweepArgs::one)
+  GlobalParams *gp;
 };
 
 constexpr int REFINE_BATCH = 64;                   // matches a warp lets build up before it drains them
@@ -1012,6 +1018,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
   const uint32_t lane = threadIdx.x & 31;
   uint32_t *q = q_all + (threadIdx.x >> 5) * REFINE_QCAP;  // (iteration << 8) | (lane << 3) | j
   uint32_t cnt = 0;  // warp-uniform
+  unsigned long long matched = 0;
   const IDX *idx = static_cast<const IDX *>(a.idx);
 
   // (Measured: a wider drain with four entries per lane in flight is slower, 225 us against 185 us
@@ -1076,13 +1083,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
 #pragma unroll
       for (int j = 0; j < PPL; ++j)
         if (mm & (1u << j)) q[e++] = (it << 8) | (lane << 3) | j;
-      cnt += __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t added = __shfl_sync(0xffffffffu, incl, 31);
+      cnt += added;
+      matched += added;
       __syncwarp();
       if (cnt >= REFINE_BATCH) drain();
     }
     cur = nxt;
   }
   drain();
+  if (lane == 0 && matched) atomicAdd(&a.gp->refine_points, matched);
   __syncthreads();
   long long *pw = a.part_w + (size_t)blockIdx.x * nslots;
   uint32_t *pm = a.part_min + (size_t)blockIdx.x * nslots;

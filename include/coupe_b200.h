@@ -48,6 +48,7 @@ typedef struct coupe_b200_stats {
 	double   matrix[9];      /* RIB: the obb_to_aabb matrix applied (row-major DxD) */
 	double   dense_sweep_ms; /* option "time_sweeps": summed device time of the dense sweeps */
 	double   refine_sweep_ms;/* option "time_sweeps": summed device time of the refinement sweeps */
+	uint64_t refine_points;  /* points re-binned by the refinement sweeps (this rank) */
 } coupe_b200_stats;
 
 /* One context per process and GPU.  `device` is a CUDA ordinal.  Returns a

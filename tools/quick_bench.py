@@ -56,7 +56,7 @@ def main():
     algo.partition(part, (pts, w))
     torch.cuda.synchronize()
     ts = []
-    for _ in range(a.reps):
+    for _ in range(max(a.reps, 0)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         algo.partition(part, (pts, w))
@@ -66,6 +66,8 @@ def main():
     st = ctx.stats()
     wbytes = {"f64": 8, "i64": 8, "i32": 4, "const": 0}[a.w]
     algo_bytes = a.n * (a.iters * (16 + wbytes) + 8 * a.dim + wbytes + 12)
+    if not ts:
+        return
     best = min(ts)
     print(f"n={a.n} dim={a.dim} iters={a.iters} w={a.w} dist={a.dist} opts={a.opt}")
     print(f"  ms: {['%.2f' % t for t in ts]}  best {best:.2f} ms -> {a.n / best / 1e3:.1f} Mpts/s, "
