@@ -258,9 +258,10 @@ void launch_sweep_any(int win, bool root, bool smem, bool tsm, bool idx16, int g
 }
 
 template <int WIN>
-void launch_refine(bool idx16, int grid, size_t bytes, cudaStream_t st, const RefineArgs &a) {
-  if (idx16) sweep_refine_kernel<WIN, uint16_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else sweep_refine_kernel<WIN, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+void launch_refine(bool idx16, bool rts, int grid, size_t bytes, cudaStream_t st, const RefineArgs &a) {
+  if (idx16) sweep_refine_kernel<WIN, uint16_t, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);  // 2^16 idx values: always staged
+  else if (rts) sweep_refine_kernel<WIN, uint32_t, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  else sweep_refine_kernel<WIN, uint32_t, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
 }
 
 void prepare_funcs(coupe_b200_ctx *c) {
@@ -279,12 +280,14 @@ void prepare_funcs(coupe_b200_ctx *c) {
   SETALL(WIN_I32, false);
   SETALL(WIN_I64, false);
   SETALL(WIN_CONST, false);
-  SETATTR((sweep_refine_kernel<WIN_I32, uint16_t>));
-  SETATTR((sweep_refine_kernel<WIN_I64, uint16_t>));
-  SETATTR((sweep_refine_kernel<WIN_CONST, uint16_t>));
-  SETATTR((sweep_refine_kernel<WIN_I32, uint32_t>));
-  SETATTR((sweep_refine_kernel<WIN_I64, uint32_t>));
-  SETATTR((sweep_refine_kernel<WIN_CONST, uint32_t>));
+#define SETREF(win)                                            \
+  SETATTR((sweep_refine_kernel<win, uint16_t, true>));         \
+  SETATTR((sweep_refine_kernel<win, uint32_t, true>));         \
+  SETATTR((sweep_refine_kernel<win, uint32_t, false>))
+  SETREF(WIN_I32);
+  SETREF(WIN_I64);
+  SETREF(WIN_CONST);
+#undef SETREF
 #undef SETALL
 #undef SETATTR
   c->funcs_ready = true;
@@ -678,9 +681,9 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
                   c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u, gp};
     time_begin(1);
     switch (win) {
-      case WIN_I32: launch_refine<WIN_I32>(idx16, sweep_grid, rbytes, st, ra); break;
-      case WIN_I64: launch_refine<WIN_I64>(idx16, sweep_grid, rbytes, st, ra); break;
-      default: launch_refine<WIN_CONST>(idx16, sweep_grid, rbytes, st, ra); break;
+      case WIN_I32: launch_refine<WIN_I32>(idx16, rts, sweep_grid, rbytes, st, ra); break;
+      case WIN_I64: launch_refine<WIN_I64>(idx16, rts, sweep_grid, rbytes, st, ra); break;
+      default: launch_refine<WIN_CONST>(idx16, rts, sweep_grid, rbytes, st, ra); break;
     }
     time_end();
     reduce_partials_kernel<<<(nslots + 31) / 32, 256, 0, st>>>(ra.part_w, ra.part_min, sweep_grid,

@@ -985,8 +985,9 @@ struct IdxVec<uint32_t> {
 // lane busy.  Matches are a few percent of the points, so without the queue nearly every
 // warp would run the expensive branch for one or two lanes at a time.  The scan itself is a
 // pure stream of 16-byte idx loads, two in flight per lane.
-template <int WIN, class IDX>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const RefineArgs a) {
+// RTS: the per-node target words are staged in shared memory (always possible with 16-bit idx words).
+template <int WIN, class IDX, bool RTS>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __grid_constant__ RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int PPL = IdxVec<IDX>::N;
   const uint32_t nslots = a.nslots;
@@ -1002,8 +1003,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
     s_hi[i] = 0;
     s_min[i] = KEY_EMPTY;
   }
-  const bool rts = a.rt_in_smem != 0;
-  if (rts)
+  if (RTS)
     for (uint32_t i = threadIdx.x; i < nodes; i += blockDim.x) {
       const uint2 rt = a.node_rt[i];
       s_tg[i] = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
@@ -1030,66 +1030,78 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const Re
       if (i >= n) continue;
       const uint32_t p = ((uint32_t)idx[i] >> k0) & (nodes - 1);
       const float x = __ldg(a.x + i);
+      const long long w = load_w1<WIN>(a.w, i, 1.0);  // issued with the coordinate, not after the bracket test
       const float4 r = __ldg(&a.rtable[p]);
-      const bool in = !(x < r.x) && (x < r.y || (r.z != 0.f && x <= r.y));
-      if (!in) continue;
       const uint32_t rank = __ldg(&a.node_rt[p]).y;
       const float2 f = __ldg(&a.rfast[p]);
+      const bool in = !(x < r.x) && (x < r.y || (r.z != 0.f && x <= r.y));
+      if (!in) continue;
       const float t = __fmul_rn(__fsub_rn(x, r.x), f.x);
       const float tf = __fadd_rd(t, 8388608.f);
       const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
       uint32_t bin = __float_as_uint(tf) & 0x7FFFFFu;
       if (!(fabsf(fr - 0.5f) < f.y)) bin = descend_exact(x, r.x, r.y, k);
-      accumulate_smem<WIN>(lo_base + ((rank << k) + bin) * 4, hi_off, min_off, load_w1<WIN>(a.w, i, 1.0),
-                           f2key(x), a.one);
+      accumulate_smem<WIN>(lo_base + ((rank << k) + bin) * 4, hi_off, min_off, w, f2key(x), a.one);
     }
     __syncwarp();
     cnt = 0;
   };
 
-  IdxVec<IDX> cur, nxt;
-  if (g_first < ngroups) cur.load(a.idx, g_first);
+  // The scan is a pure stream of 16-byte loads with little work per load: four loads per lane are
+  // kept in flight (a ring of four register buffers), otherwise each warp waits a full memory
+  // latency per 512 bytes and the pass runs at a third of the HBM rate.
+  constexpr int DEPTH = 4;
+  IdxVec<IDX> buf[DEPTH];
+#pragma unroll
+  for (int u = 0; u < DEPTH; ++u)
+    if (g_first + (size_t)u * stride < ngroups) buf[u].load(a.idx, g_first + (size_t)u * stride);
   // every lane of a warp runs the same number of iterations (the warp's first lane decides)
   const size_t g_warp = g_first - lane;
   uint32_t it = 0;
-  for (size_t gw = g_warp; gw < ngroups; gw += stride, ++it) {
-    const size_t g = gw + lane;
-    if (g + stride < ngroups) nxt.load(a.idx, g + stride);
-    uint32_t mm = 0;  // which of the lane's points match
-    if (g < ngroups) {
-      uint32_t v[PPL];
-      cur.get(v);
+  for (size_t gw = g_warp; gw < ngroups; gw += (size_t)DEPTH * stride) {
 #pragma unroll
-      for (int j = 0; j < PPL; ++j) {
-        const uint32_t pn = (v[j] >> k0) & (nodes - 1);  // masked: the padding past n holds anything
-        uint32_t tg;
-        if (rts) tg = s_tg[pn];
-        else {
-          const uint2 rt = __ldg(&a.node_rt[pn]);
-          tg = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
+    for (int u = 0; u < DEPTH; ++u) {
+      const size_t gwu = gw + (size_t)u * stride;
+      if (gwu >= ngroups) break;  // warp-uniform
+      const size_t g = gwu + lane;
+      const IdxVec<IDX> cur = buf[u];
+      if (g + (size_t)DEPTH * stride < ngroups) buf[u].load(a.idx, g + (size_t)DEPTH * stride);
+      uint32_t mm = 0;  // which of the lane's points match
+      if (g < ngroups) {
+        uint32_t v[PPL];
+        cur.get(v);
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+          const uint32_t pn = (v[j] >> k0) & (nodes - 1);  // masked: the padding past n holds anything
+          uint32_t tg;
+          if (RTS) tg = s_tg[pn];
+          else {
+            const uint2 rt = __ldg(&a.node_rt[pn]);
+            tg = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
+          }
+          mm |= (v[j] == tg ? 1u : 0u) << j;
         }
-        if (v[j] == tg) mm |= 1u << j;
       }
-    }
-    if (__any_sync(0xffffffffu, mm != 0)) {
-      const uint32_t c = __popc(mm);
-      uint32_t incl = c;  // inclusive warp scan of the match counts
+      if (__any_sync(0xffffffffu, mm != 0)) {
+        const uint32_t c = __popc(mm);
+        uint32_t incl = c;  // inclusive warp scan of the match counts
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += o;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= (uint32_t)d) incl += o;
+        }
+        uint32_t e = cnt + incl - c;
+#pragma unroll
+        for (int j = 0; j < PPL; ++j)
+          if (mm & (1u << j)) q[e++] = (it << 8) | (lane << 3) | j;
+        const uint32_t added = __shfl_sync(0xffffffffu, incl, 31);
+        cnt += added;
+        matched += added;
+        __syncwarp();
+        if (cnt >= REFINE_BATCH) drain();
       }
-      uint32_t e = cnt + incl - c;
-#pragma unroll
-      for (int j = 0; j < PPL; ++j)
-        if (mm & (1u << j)) q[e++] = (it << 8) | (lane << 3) | j;
-      const uint32_t added = __shfl_sync(0xffffffffu, incl, 31);
-      cnt += added;
-      matched += added;
-      __syncwarp();
-      if (cnt >= REFINE_BATCH) drain();
+      ++it;
     }
-    cur = nxt;
   }
   drain();
   if (lane == 0 && matched) atomicAdd(&a.gp->refine_points, matched);
