@@ -34,7 +34,7 @@ fn main() {
         println!("cargo:rustc-link-search=native={}", root.join("coupe_b200/lib").display());
     }
     println!("cargo:rustc-link-lib=dylib=coupe_b200");
-    for f in ["engine.cu", "ffi.cu", "rcb_kernels.cuh"] {
+    for f in ["engine.cu", "ffi.cu", "tools.cu", "rcb_kernels.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/coupe_b200.h").display());

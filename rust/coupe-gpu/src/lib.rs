@@ -16,6 +16,8 @@ use std::os::raw::{c_char, c_int};
 
 use coupe::{Partition, PointND};
 
+pub mod tools;
+
 #[repr(C)]
 pub struct Ctx {
     _private: [u8; 0],
