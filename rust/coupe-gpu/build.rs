@@ -25,6 +25,7 @@ fn main() {
             .arg(&lib)
             .arg(csrc.join("engine.cu"))
             .arg(csrc.join("ffi.cu"))
+            .arg(csrc.join("tools.cu"))
             .args(["-ldl", "-lpthread"])
             .status()
             .expect("nvcc not found: set NVCC or enable the `prebuilt` feature");
