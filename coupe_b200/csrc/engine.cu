@@ -210,6 +210,7 @@ struct coupe_b200_ctx {
   unsigned int *xchg_aux = nullptr;                       // {ticket, error}
   // options
   int kmax_a = 8, nb_smem_log2 = 14, kmax_refine = 10, force_global = 0, trace_on = 1, time_sweeps = 0;
+  int sample_w_opt = 1;  // f64 weights: max |w| from a sample, verified by the root sweep
   std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
   std::vector<int> event_kind;      // 0 dense, 1 refine
   // last call
@@ -473,13 +474,14 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const size_t ngroups = (n + 3) / 4;
     const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 8, (ngroups + 255) / 256));
     const double *wf = (wtype == WT_F64 && w_dev) ? static_cast<const double *>(w_dev) : nullptr;
+    const int ws = c->sample_w_opt ? 1 : 0;
     const int pa = ((uintptr_t)pts % 16) == 0, wa = ((uintptr_t)w_dev % 16) == 0;
     if (D == 2) {
-      if (rib) narrow_kernel<2, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
-      else narrow_kernel<2, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
+      if (rib) narrow_kernel<2, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
+      else narrow_kernel<2, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
     } else {
-      if (rib) narrow_kernel<3, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
-      else narrow_kernel<3, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa);
+      if (rib) narrow_kernel<3, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
+      else narrow_kernel<3, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
     }
     R.launched();
     if (c->world > 1) {
@@ -503,9 +505,14 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   float *tsp_cur = c->tsp_a.as<float>(), *tsp_next = c->tsp_b.as<float>();
   float4 *rtable = c->rtable.as<float4>();
   uint32_t *target = c->target.as<uint32_t>();
-  init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, thi_cur, plan_first(c, 0).k, D, wtype,
-                                    w_is_const, wconst_i, wconst_f, n_global);
-  R.launched();
+  // max |w| of f64 array weights comes from a sample; the root sweep verifies the exponent
+  const bool verify_scale = c->sample_w_opt && wtype == WT_F64 && !w_is_const;
+  auto enqueue_init_root = [&]() {
+    init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, thi_cur, plan_first(c, 0).k, D, wtype,
+                                      w_is_const, wconst_i, wconst_f, n_global);
+    R.launched();
+  };
+  enqueue_init_root();
 
   const size_t ngroups = (n + 3) / 4;
   const int sweep_grid =
@@ -584,7 +591,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   // whether level l needs refinement; its kernels return at once when it does
   // (gp->unresolved != 0) and the pass is enqueued again after the refinement.
   const uint32_t *guard_ptr = &gp->unresolved;
-  uint32_t w_wide = 0;
+  uint32_t w_wide = 0, rescale = 0;
   uint64_t seq = c->flag_seq;
   auto flag_slot = [&](uint64_t s) { return s % FLAG_SLOTS; };
   auto wait_flag = [&](uint64_t s) -> uint32_t {
@@ -600,6 +607,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     S.flag_waits += 1;
     if (v & FLAG_ABORTED) throw CudaFail{cudaErrorUnknown, "waited on an aborted pass"};
     w_wide = (uint32_t)(v >> 32) & 1u;
+    rescale = (uint32_t)(v >> 33) & 1u;
     return (uint32_t)v;
   };
   // walk + rank of one pass; returns the sequence number of its flag
@@ -611,7 +619,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
                 tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
                 plan_first(c, level + 1).k, rfast, refine_cap(level, rts_, rtb_), c->kmax_refine,
-                c->d_flags + flag_slot(s), make_xchg(s)};
+                verify_scale ? 1 : 0, c->d_flags + flag_slot(s), make_xchg(s)};
     const size_t bytes = ((size_t)2 << k) * 12;
     const uint32_t nodes = 1u << level;
     // the last block to finish ranks the undecided nodes and reports to the host flag
@@ -665,6 +673,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       R.launched();
     }
     allreduce_hist(nb);
+    if (level == 0 && verify_scale) R.allreduce(&gp->maxabs_true_bits, 1, ncclUint64, ncclMax);
     return enqueue_walk(level, k, k, 1, 0, guard);
   };
   auto enqueue_refine_round = [&](int level, int k0, uint32_t unresolved) {
@@ -715,20 +724,40 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   for (int level = 0; level < L; ++level) {
     const int k = plan_first(c, level).k;
     // i64 weights: which column the later sweeps read is only known after the root pass
-    const bool can_speculate = !(level == 0 && w32 && wtype == WT_I64);
+    const bool can_speculate = !(level == 0 && ((w32 && wtype == WT_I64) || verify_scale));
     advance_level();
     bool speculated = false;
     uint64_t next_pending = 0;
+    int win_root = win;
+    const void *wp_root = wp;
+    if (level == 0 && w32 && wtype != WT_I64) {  // f64 (and unaligned i32) weights: always narrowed
+      win = WIN_I32;
+      wp = w32;
+    }
     if (can_speculate) {
-      if (level == 0 && w32) {  // f64 weights: always narrowed
-        win = WIN_I32;
-        wp = w32;
-      }
       if (level + 1 < L) next_pending = enqueue_first_pass(level + 1, k, guard_ptr);
       else enqueue_emit(k, guard_ptr);
       speculated = true;
     }
     uint32_t unresolved = wait_flag(pending);
+    if (level == 0 && rescale) {
+      // the sample missed the exponent of max |w| (an outlier weight): take the true maximum the root
+      // sweep computed and redo the root pass; every rank sees the same flag
+      advance_level();  // back to the root's tables
+      CU(cudaMemcpyAsync(&gp->maxabs_bits, &gp->maxabs_true_bits, 8, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemsetAsync(&gp->rescale, 0, 4, st));
+      enqueue_init_root();
+      S.dense_sweeps -= 1;
+      S.weight_rescales += 1;
+      std::swap(win, win_root);  // the root sweep reads the caller's f64 column
+      std::swap(wp, wp_root);
+      pending = enqueue_first_pass(0, 0, nullptr);
+      std::swap(win, win_root);
+      std::swap(wp, wp_root);
+      advance_level();
+      unresolved = wait_flag(pending);
+      if (rescale) return COUPE_ERR_CRASH;  // cannot happen: the scale now comes from the true maximum
+    }
     if (level == 0 && w32 && wtype == WT_I64) {
       if (c->world > 1) {  // every rank must take the same path
         R.allreduce(&gp->w_wide, 1, ncclUint32, ncclMax);
@@ -1037,6 +1066,7 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "trace") c->trace_on = value != 0;
   else if (s == "time_sweeps") c->time_sweeps = (int)value;
   else if (s == "peer_exchange") c->use_xchg_opt = value != 0;
+  else if (s == "sample_weights") c->sample_w_opt = value != 0;
   else return COUPE_ERR_NOT_FOUND;
   return COUPE_ERR_OK;
 }

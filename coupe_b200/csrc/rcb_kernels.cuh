@@ -50,13 +50,15 @@ struct GlobalParams {
   double q;                        // 2^-shift: value of one fixed-point unit
   double scale;                    // 2^shift
   unsigned long long n_global;     // points over all ranks
-  unsigned long long maxabs_bits;  // bit pattern of max |w| (f64 weights)
+  unsigned long long maxabs_bits;  // bit pattern of max |w| (f64 weights): from a SAMPLE of the weights at first
+  unsigned long long maxabs_true_bits;  // ... over all weights, computed by the root sweep while it quantises
   long long wconst;                // constant weight in accumulator units
   uint32_t bbox_keys[8];           // [0..D) min keys, [4..4+D) inverted max keys
   uint32_t unresolved;             // nodes whose bisection needs another pass
   uint32_t w_wide;                 // some i64 weight does not fit the narrowed i32 column
   uint32_t leaf_min;               // smallest non-empty leaf path
   uint32_t walk_ticket;            // blocks of the current walk launch that are done (reset by the last one)
+  uint32_t rescale;                // the sampled max |w| gave another fixed-point shift than the true one: redo the root pass
   unsigned long long refine_points;  // points the refinement sweeps of the call re-binned (statistics)
   int shift;
 };
@@ -119,7 +121,7 @@ template <int D, bool ROT>
 __global__ void __launch_bounds__(256)
 narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
               float *__restrict__ x1, float *__restrict__ x2, Mat3 rot, GlobalParams *gp,
-              const double *__restrict__ wf64, int pts_aligned, int w_aligned) {
+              const double *__restrict__ wf64, int pts_aligned, int w_aligned, int w_sample) {
   float mn[D], mx[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
@@ -178,7 +180,10 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
     if (D == 3)
       __stcs(reinterpret_cast<float4 *>(x2 + i0),
              make_float4(o[D - 1][0], o[D - 1][1], o[D - 1][2], o[D - 1][3]));
-    if (wf64) {
+    // max |w| only fixes the exponent of the fixed-point scale: with w_sample set, one run of 256
+    // groups in 64 is read here (block-uniform test) and the root sweep, which reads every weight
+    // anyway, verifies the exponent (GlobalParams::rescale)
+    if (wf64 && (!w_sample || ((g >> 8) & 63) == 0)) {
       if (full && w_aligned) {
         const double2 a = __ldcs(reinterpret_cast<const double2 *>(wf64 + i0));
         const double2 b = __ldcs(reinterpret_cast<const double2 *>(wf64 + i0) + 1);
@@ -234,6 +239,16 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
   }
 }
 
+// Fixed-point shift for f64 weights: min(31 - e, 62 - e - nbits), max|w| < 2^e, n <= 2^nbits.
+__device__ inline int fixed_point_shift(double maxabs, unsigned long long n_global) {
+  if (!(maxabs > 0.0 && maxabs <= 1.7976931348623157e308)) return 0;
+  int e;
+  frexp(maxabs, &e);
+  int nbits = 0;
+  while (nbits < 63 && (1ull << nbits) < n_global) ++nbits;
+  return max(-1000, min(1000, min(31 - e, 62 - e - nbits)));
+}
+
 // ---------------------------------------------------------------------------
 // Root set-up once the (all-reduced) bounding box and max |w| are known.
 // ---------------------------------------------------------------------------
@@ -245,18 +260,9 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   gp->n_global = n_global;
   // fixed-point shift for f64 weights: min(31 - e, 62 - e - nbits), max|w| < 2^e, n <= 2^nbits
   int shift = 0;
-  double maxabs = 0.0;
-  if (wtype == WT_F64) {
-    maxabs = w_is_const ? fabs(wconst_f) : __longlong_as_double((long long)gp->maxabs_bits);
-    if (maxabs > 0.0 && maxabs <= 1.7976931348623157e308) {
-      int e;
-      frexp(maxabs, &e);
-      int nbits = 0;
-      while (nbits < 63 && (1ull << nbits) < n_global) ++nbits;
-      shift = min(31 - e, 62 - e - nbits);
-      shift = max(-1000, min(1000, shift));
-    }
-  }
+  if (wtype == WT_F64)
+    shift = fixed_point_shift(w_is_const ? fabs(wconst_f) : __longlong_as_double((long long)gp->maxabs_bits),
+                              n_global);
   gp->shift = shift;
   gp->scale = ldexp(1.0, shift);
   gp->q = ldexp(1.0, -shift);
@@ -457,6 +463,7 @@ template <>
 struct RawW4<WIN_CONST> {
   __device__ __forceinline__ void load(const void *, size_t, bool) {}
   __device__ __forceinline__ void get(double, long long (&o)[4]) const { o[0] = o[1] = o[2] = o[3] = 1; }
+  __device__ __forceinline__ double maxabs() const { return 0.0; }
 };
 template <>
 struct RawW4<WIN_I32> {
@@ -469,6 +476,7 @@ struct RawW4<WIN_I32> {
   __device__ __forceinline__ void get(double, long long (&o)[4]) const {
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
   }
+  __device__ __forceinline__ double maxabs() const { return 0.0; }
 };
 template <>
 struct RawW4<WIN_I64> {
@@ -486,6 +494,7 @@ struct RawW4<WIN_I64> {
   __device__ __forceinline__ void get(double, long long (&o)[4]) const {
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
   }
+  __device__ __forceinline__ double maxabs() const { return 0.0; }
 };
 template <>
 struct RawW4<WIN_F64> {
@@ -503,6 +512,9 @@ struct RawW4<WIN_F64> {
   __device__ __forceinline__ void get(double scale, long long (&o)[4]) const {
     o[0] = quantise_f64(a.x, scale); o[1] = quantise_f64(a.y, scale);
     o[2] = quantise_f64(b.x, scale); o[3] = quantise_f64(b.y, scale);
+  }
+  __device__ __forceinline__ double maxabs() const {
+    return fmax(fmax(fabs(a.x), fabs(a.y)), fmax(fabs(b.x), fabs(b.y)));
   }
 };
 
@@ -637,6 +649,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   const bool vec = (ROOT || WIN == WIN_I64) ? a.w_vec != 0 : true;
   const bool narrow = ROOT && WIN != WIN_CONST && a.w32_out != nullptr;
   bool wide = false;  // some i64 weight does not fit the narrowed i32 column
+  double wmax = 0.0;  // root sweep over f64 weights: the true max |w| (verifies the sampled exponent)
   const uint32_t kbit = 1u << k;
   // slot = (parent << (k+1)) + child * 2^k + bin; the bin comes out of the float trick below as
   // bits(tf) = 0x4B000000 + bin, so the constant is folded into the child term
@@ -702,6 +715,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     Idx4<IDX>::store(a.idx, i0, slot);
     long long w[4];
     cur.w.get(scale, w);
+    if (ROOT && WIN == WIN_F64) wmax = fmax(wmax, cur.w.maxabs());
     if (narrow) {
       __stcs(reinterpret_cast<int4 *>(a.w32_out + i0),
              make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
@@ -782,6 +796,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       const uint32_t slot = slot_exact(a, pv, x, i, ROOT);
       static_cast<IDX *>(a.idx)[i] = (IDX)slot;
       const long long w = load_w1<WIN>(a.w, i, scale);
+      if (ROOT && WIN == WIN_F64) wmax = fmax(wmax, fabs(static_cast<const double *>(a.w)[i]));
       if (narrow) {
         a.w32_out[i] = (int)w;
         if (WIN == WIN_I64) wide = wide || w != (int)w;
@@ -791,6 +806,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     }
   }
   if (ROOT && WIN == WIN_I64 && wide) a.gp->w_wide = 1;
+  if (ROOT && WIN == WIN_F64) {  // bit patterns of non-negative doubles order like unsigned integers
+    unsigned long long wb = (unsigned long long)__double_as_longlong(wmax);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, wb, sh);
+      wb = o > wb ? o : wb;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(&a.gp->maxabs_true_bits, wb);
+  }
   if (SMEM) {
     __syncthreads();
     long long *pw = a.part_w + (size_t)blockIdx.x * nb;
@@ -1170,7 +1194,7 @@ __device__ void rank_unresolved_block(const uint32_t *target, uint32_t nodes, ui
   if (threadIdx.x == 0) {  // the host polls this word (mapped pinned memory) instead of synchronising
     gp->unresolved = unresolved;
     __threadfence();
-    *host_flag = FLAG_VALID | ((unsigned long long)gp->w_wide << 32) | unresolved;
+    *host_flag = FLAG_VALID | ((unsigned long long)(gp->rescale & 1u) << 33) | ((unsigned long long)gp->w_wide << 32) | unresolved;
     __threadfence_system();
   }
 }
@@ -1231,6 +1255,7 @@ struct WalkArgs {
   float2 *rfast;             // per node: fast binning parameters of the next refinement pass
   uint32_t refine_cap;       // histogram slots a refinement pass may use at this level
   int kmax_refine;
+  int verify_scale;          // level 0, f64 weights: max |w| was sampled (GlobalParams::rescale)
   volatile unsigned long long *host_flag;  // mapped host word the pass reports to
   Xchg x;                    // multi-GPU: read the histogram from the exchange buffer (world > 1)
 };
@@ -1326,6 +1351,11 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     hi_incl = 1;
     below_nonempty = 0;
     if (a.level == 0) ns.sum = O::canon((long long)wtree[1]);  // :684, total weight
+    if (a.level == 0 && WT == WT_F64 && !a.w_is_const && a.verify_scale) {
+      // the scale came from a sample of the weights: the true maximum (root sweep) must give the same shift
+      const int want = fixed_point_shift(__longlong_as_double((long long)a.gp->maxabs_true_bits), a.gp->n_global);
+      if (want != a.gp->shift) a.gp->rescale = 1;
+    }
   } else {
     lo = ns.lo; hi = ns.hi;
     w_below = ns.w_below;

@@ -223,6 +223,36 @@ def test_rcb_f64_weights(cb, oracle, n, dim, pk, iters, tol):
     assert oracle.imbalance(nparts, got, w) == pytest.approx(oracle.imbalance(nparts, want_nat, w), rel=1e-9)
 
 
+def test_f64_weight_scale_from_sample_is_verified(cb, oracle):
+    """max |w| is read from a sample of the weights (one run of 1024 points in 64); the root sweep checks
+    the exponent against the true maximum and the root pass is redone when an outlier was missed."""
+    rng = np.random.default_rng(31)
+    n = 300_000
+    pts = rng.normal(size=(n, 3))
+    w = rng.uniform(0.5, 1.5, n)
+    ctx = cb.Context(0)
+    want = oracle.rcb(pts, w, 7, 0.02, mode=1)
+    assert np.array_equal(run_device(cb, pts, w, 7, 0.02, ctx=ctx), want)
+    assert ctx.stats()["weight_rescales"] == 0
+    for at, val in ((5000, 1000.0), (70_000, 3.0), (123_457, 1e12)):  # not in a sampled run: 0..1023, 65536..66559, ...
+        w2 = w.copy()
+        w2[at] = val
+        want = oracle.rcb(pts, w2, 7, 0.02, mode=1)
+        assert np.array_equal(run_device(cb, pts, w2, 7, 0.02, ctx=ctx), want)
+        assert ctx.stats()["weight_rescales"] == 1
+        assert ctx.stats()["weight_shift"] == oracle.fix_shift(n, w2.max())
+    w3 = w.copy()
+    w3[100] = 64.0  # inside the first sampled run: the sample already has the right exponent
+    assert np.array_equal(run_device(cb, pts, w3, 7, 0.02, ctx=ctx), oracle.rcb(pts, w3, 7, 0.02, mode=1))
+    assert ctx.stats()["weight_rescales"] == 0
+    ctx.set_option("sample_weights", 0)
+    w2 = w.copy()
+    w2[5000] = 1000.0
+    assert np.array_equal(run_device(cb, pts, w2, 7, 0.02, ctx=ctx), oracle.rcb(pts, w2, 7, 0.02, mode=1))
+    assert ctx.stats()["weight_rescales"] == 0
+    ctx.close()
+
+
 def test_const_f64_non_dyadic_weight(cb, oracle):
     rng = np.random.default_rng(4)
     pts = gen_points(rng, 70_001, 3, "gauss")
