@@ -81,6 +81,7 @@ def two_gpus():
     ("f64", 3, 9, 0.05, False),
     ("i64big", 2, 8, 0.001, False),
     ("const", 2, 7, 0.0, True),
+    ("f64outlier", 3, 8, 0.05, False),  # one huge weight on the second rank, outside every sampled run
 ])
 def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, empty_last, peer):
     rng = np.random.default_rng(11)
@@ -90,6 +91,7 @@ def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, em
     w = {"i64": rng.integers(1, 100, n).astype(np.int64),
          "i64big": rng.integers(1, 2**40, n).astype(np.int64),
          "f64": rng.uniform(0.5, 1.5, n),
+         "f64outlier": np.where(np.arange(n) == n - 77_777, 1e9, rng.uniform(0.5, 1.5, n)),
          "const": np.array(3, dtype=np.int32)}[wkind]
     got = run_sharded((pts, w, iters, tol, False, empty_last, peer))
     assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=1))
