@@ -96,6 +96,95 @@ bool materialise(const coupe_data *d, size_t elem, std::vector<unsigned char> &o
   return true;
 }
 
+// ---- host <-> device copies of caller-owned arrays ------------------------------------------
+// Callers of the reference hand over plain (pageable) memory.  cudaMemcpy on pageable memory is a
+// single-threaded bounce through the driver's staging buffer (10-20 GB/s); here several host
+// threads each own two pinned buffers and a stream and move alternate chunks: memcpy into (out
+// of) pinned memory overlaps the DMA of the other buffer and the threads together keep the link
+// busy.  Memory the caller has pinned itself (cudaHostAlloc / cudaHostRegister) goes straight
+// through one cudaMemcpy.
+constexpr size_t STAGE_CHUNK = 8u << 20;  // bytes per pinned buffer
+constexpr unsigned STAGE_THREADS = 8;
+
+struct StageLane {
+  void *buf[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+  bool ok() const { return buf[0] && buf[1] && done[0] && done[1] && stream; }
+};
+StageLane g_lanes[STAGE_THREADS];
+bool g_lanes_ready = false;
+
+bool ensure_lanes() {
+  if (g_lanes_ready) return true;
+  for (StageLane &l : g_lanes) {
+    for (int b = 0; b < 2; ++b) {
+      if (cudaHostAlloc(&l.buf[b], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&l.done[b], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+  }
+  g_lanes_ready = true;
+  return true;
+}
+
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// to_device: host -> dev, else dev -> host.  Returns false on any CUDA failure.
+bool staged_copy(void *dev, void *host, size_t bytes, bool to_device, int device) {
+  if (bytes == 0) return true;
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  static const bool no_staging = [] { const char *e = getenv("COUPE_B200_NO_STAGING"); return e && *e && *e != '0'; }();
+  if (no_staging || bytes < 4 * STAGE_CHUNK || is_pinned(host) || !ensure_lanes())
+    return cudaMemcpy(to_device ? dev : host, to_device ? host : dev, bytes, kind) == cudaSuccess;
+  const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  const unsigned nt = (unsigned)std::min<size_t>(STAGE_THREADS, nchunks);
+  bool ok[STAGE_THREADS];
+  auto work = [&](unsigned t) {
+    ok[t] = cudaSetDevice(device) == cudaSuccess;
+    StageLane &l = g_lanes[t];
+    int b = 0;
+    size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
+    for (size_t c = t; c < nchunks && ok[t]; c += nt, b ^= 1) {
+      const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+      // the buffer's previous transfer must be over (and, device -> host, copied out) before it is reused
+      if (pending_len[b]) {
+        ok[t] = cudaEventSynchronize(l.done[b]) == cudaSuccess;
+        if (!to_device) memcpy(static_cast<char *>(host) + pending_off[b], l.buf[b], pending_len[b]);
+      }
+      if (to_device) {
+        memcpy(l.buf[b], static_cast<const char *>(host) + off, len);
+        ok[t] = ok[t] && cudaMemcpyAsync(static_cast<char *>(dev) + off, l.buf[b], len, kind, l.stream) == cudaSuccess;
+      } else {
+        ok[t] = ok[t] && cudaMemcpyAsync(l.buf[b], static_cast<const char *>(dev) + off, len, kind, l.stream) == cudaSuccess;
+      }
+      ok[t] = ok[t] && cudaEventRecord(l.done[b], l.stream) == cudaSuccess;
+      pending_off[b] = off;
+      pending_len[b] = len;
+    }
+    for (int q = 0; q < 2; ++q)
+      if (pending_len[q]) {
+        ok[t] = cudaEventSynchronize(l.done[q]) == cudaSuccess && ok[t];
+        if (!to_device) memcpy(static_cast<char *>(host) + pending_off[q], l.buf[q], pending_len[q]);
+      }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+  bool all = true;
+  for (unsigned t = 0; t < nt; ++t) all = all && ok[t];
+  if (!all) cudaGetLastError();
+  return all;
+}
+
 // Host arrays in, host part ids out: copy to the device, run the CUDA path, copy back.
 // Caller holds g_mu.
 int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dimension, uintptr_t n,
@@ -110,18 +199,17 @@ int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dime
   const size_t welem = wtype == COUPE_INT ? 4 : 8;
   if (!sg.pts.ensure(n * pelem) || !sg.part.ensure(n * sizeof(uint64_t))) return COUPE_ERR_ALLOC;
   if (w_host && !sg.w.ensure(n * welem)) return COUPE_ERR_ALLOC;
-  if (cudaMemcpy(sg.pts.p, pts_host, n * pelem, cudaMemcpyHostToDevice) != cudaSuccess)
-    return COUPE_ERR_CRASH;
-  if (w_host && cudaMemcpy(sg.w.p, w_host, n * welem, cudaMemcpyHostToDevice) != cudaSuccess)
-    return COUPE_ERR_CRASH;
+  const int device = coupe_b200_ctx_device(ctx);
+  if (cudaSetDevice(device) != cudaSuccess) return COUPE_ERR_CRASH;
+  if (!staged_copy(sg.pts.p, const_cast<double *>(pts_host), n * pelem, true, device)) return COUPE_ERR_CRASH;
+  if (w_host && !staged_copy(sg.w.p, const_cast<void *>(w_host), n * welem, true, device)) return COUPE_ERR_CRASH;
   auto fn = rib ? coupe_b200_rib_device : coupe_b200_rcb_device;
   const int err = fn(ctx, nullptr, static_cast<uint64_t *>(sg.part.p), dimension, n,
                      static_cast<const double *>(sg.pts.p), wtype, w_host ? sg.w.p : nullptr, w_const,
                      iter_count, tolerance);
   if (err != COUPE_ERR_OK) return err;
   static_assert(sizeof(uintptr_t) == sizeof(uint64_t), "usize is 64 bit");
-  if (cudaMemcpy(partition, sg.part.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-    return COUPE_ERR_CRASH;
+  if (!staged_copy(sg.part.p, partition, n * sizeof(uint64_t), false, device)) return COUPE_ERR_CRASH;
   return COUPE_ERR_OK;
 }
 

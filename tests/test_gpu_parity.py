@@ -350,6 +350,27 @@ def test_rib_against_oracle(cb, oracle, dim):
     assert np.array_equal(got, oracle.rcb(mapped, w, 6, 0.05))
 
 
+@pytest.mark.parametrize("n,dim,pk,wk,iters,tol", [
+    (4_000_003, 3, "cluster", "f64", 10, 0.05),   # full 148-block grid, refinement sweeps, f64 fixed point
+    (3_000_001, 2, "uniform", "i64", 12, 0.05),   # config C2 in miniature: 4096 parts, bit-exact integer weights
+    (2_500_000, 3, "grid", "f64int", 10, 0.001),  # config C3's shape: heavy coordinate duplication, tight tolerance
+])
+def test_full_grid_sizes_against_oracle(cb, oracle, n, dim, pk, wk, iters, tol):
+    rng = np.random.default_rng(n % 1000)
+    pts = gen_points(rng, n, dim, pk)
+    w = gen_weights(rng, n, wk)
+    want, tr = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
+    ctx = cb.Context(0)
+    got = run_device(cb, pts, w, iters, tol, ctx=ctx)
+    assert np.array_equal(got, want)
+    t = ctx.trace(iters)
+    v = tr.visited.astype(bool)
+    assert np.array_equal(t["visited"], tr.visited)
+    assert np.array_equal(t["split_pos"][v], tr.split_pos[v])
+    assert np.array_equal(t["iters"][v], tr.iters[v])
+    ctx.close()
+
+
 def test_large_size_properties(cb, oracle):
     """Size-independent properties at a size the oracle does not run in a test:
     every part is a box in (x, y, z) order statistics, ids dense in [0, 2^L),
