@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--dist", default="uniform", choices=["uniform", "gauss", "grid"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--rib", action="store_true")
+    ap.add_argument("--aniso", action="store_true", help="C5 shape: Gaussian sigma (10, 1, 0.1), rotated")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
@@ -37,6 +39,15 @@ def main():
         del i
     else:
         pts = torch.randn((a.n, a.dim), dtype=torch.float64, device=dev, generator=g)
+    if a.aniso:  # C5: sigma = (10, 1, 0.1), Euler rotation 30/45/60 degrees
+        import math
+        pts *= torch.tensor([10.0, 1.0, 0.1][:a.dim], dtype=torch.float64, device=dev)
+        if a.dim == 3:
+            ca, sa, cb, sb, cc, sc = (f(math.radians(d)) for d in (30, 45, 60) for f in (math.cos, math.sin))
+            rz = torch.tensor([[ca, -sa, 0], [sa, ca, 0], [0, 0, 1]], dtype=torch.float64, device=dev)
+            ry = torch.tensor([[cb, 0, sb], [0, 1, 0], [-sb, 0, cb]], dtype=torch.float64, device=dev)
+            rx = torch.tensor([[1, 0, 0], [0, cc, -sc], [0, sc, cc]], dtype=torch.float64, device=dev)
+            pts = (pts @ (rz @ ry @ rx).T).contiguous()
     if a.w == "f64" and a.dist == "grid":  # weight-gen "linear,x,0,100"
         w = (pts[:, 0] - 0.5) * (100.0 / 399.0)
     elif a.w == "f64":
@@ -52,7 +63,7 @@ def main():
     for o in a.opt:
         k, v = o.split("=")
         ctx.set_option(k, int(v))
-    algo = coupe_b200.Rcb(a.iters, a.tol, ctx)
+    algo = (coupe_b200.Rib if a.rib else coupe_b200.Rcb)(a.iters, a.tol, ctx)
     algo.partition(part, (pts, w))
     torch.cuda.synchronize()
     ts = []
