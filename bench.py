@@ -311,6 +311,12 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": algo_bytes_per_launch, "launches_timed": dense_n,
         "avg_launch_ms": dense_ms / dense_n if dense_n else None,
         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        # the algorithmic figure (coordinates and weights as supplied, 24 B per point and level) is
+        # twice what the kernel really moves (narrowed columns, 12 B): both fractions are reported
+        "achieved_on_real_traffic": (traffic["dram_bytes_per_launch"] * dense_n / (dense_ms * 1e-3) / 1e9
+                                     if traffic and dense_ms > 0 else None),
+        "frac_on_real_traffic": (traffic["dram_bytes_per_launch"] * dense_n / (dense_ms * 1e-3) / 1e9 / peak
+                                 if traffic and dense_ms > 0 else None),
         "traffic_note": traffic["note"] if traffic else "no ncu capture committed yet",
         "whole_call": {
             "algorithmic_bytes": n * (ITERS * 24 + 8 * DIM + 8 + 12),

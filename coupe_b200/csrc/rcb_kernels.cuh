@@ -975,7 +975,7 @@ struct RefineArgs {
 };
 
 constexpr int REFINE_BATCH = 64;                   // matches a warp lets build up before it drains them
-constexpr int REFINE_QCAP = REFINE_BATCH + 8 * 32;  // + what one warp iteration can add
+constexpr int REFINE_QCAP = REFINE_BATCH + 8 * 32;  // a warp appends the matches of 1024 points at a time; beyond this, no queue
 constexpr int REFINE_QBYTES = (SWEEP_THREADS / 32) * REFINE_QCAP * 4;
 
 // One 16-byte load of idx words per lane and iteration: 8 points (u16) or 4 (u32).
@@ -1045,27 +1045,30 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __
   unsigned long long matched = 0;
   const IDX *idx = static_cast<const IDX *>(a.idx);
 
+  // One matched point: bracket test, fine bin, ranked shared-memory histogram.
+  auto rebin = [&](size_t i) {
+    const uint32_t p = ((uint32_t)idx[i] >> k0) & (nodes - 1);
+    const float x = __ldg(a.x + i);
+    const long long w = load_w1<WIN>(a.w, i, 1.0);  // issued with the coordinate, not after the bracket test
+    const float4 r = __ldg(&a.rtable[p]);
+    const uint32_t rank = __ldg(&a.node_rt[p]).y;
+    const float2 f = __ldg(&a.rfast[p]);
+    const bool in = !(x < r.x) && (x < r.y || (r.z != 0.f && x <= r.y));
+    if (!in) return;
+    const float t = __fmul_rn(__fsub_rn(x, r.x), f.x);
+    const float tf = __fadd_rd(t, 8388608.f);
+    const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
+    uint32_t bin = __float_as_uint(tf) & 0x7FFFFFu;
+    if (!(fabsf(fr - 0.5f) < f.y)) bin = descend_exact(x, r.x, r.y, k);
+    accumulate_smem<WIN>(lo_base + ((rank << k) + bin) * 4, hi_off, min_off, w, f2key(x), a.one);
+  };
   // (Measured: a wider drain with four entries per lane in flight is slower, 225 us against 185 us
-  // per pass on the C4 shard — the pass is bound by the 32-byte sectors its gathers touch.)
+  // per pass on the C4 shard.)
   auto drain = [&]() {
     for (uint32_t e = lane; e < cnt; e += 32) {
       const uint32_t en = q[e];
       const size_t i = (g_first - lane + (size_t)(en >> 8) * stride + ((en >> 3) & 31)) * PPL + (en & 7);
-      if (i >= n) continue;
-      const uint32_t p = ((uint32_t)idx[i] >> k0) & (nodes - 1);
-      const float x = __ldg(a.x + i);
-      const long long w = load_w1<WIN>(a.w, i, 1.0);  // issued with the coordinate, not after the bracket test
-      const float4 r = __ldg(&a.rtable[p]);
-      const uint32_t rank = __ldg(&a.node_rt[p]).y;
-      const float2 f = __ldg(&a.rfast[p]);
-      const bool in = !(x < r.x) && (x < r.y || (r.z != 0.f && x <= r.y));
-      if (!in) continue;
-      const float t = __fmul_rn(__fsub_rn(x, r.x), f.x);
-      const float tf = __fadd_rd(t, 8388608.f);
-      const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
-      uint32_t bin = __float_as_uint(tf) & 0x7FFFFFu;
-      if (!(fabsf(fr - 0.5f) < f.y)) bin = descend_exact(x, r.x, r.y, k);
-      accumulate_smem<WIN>(lo_base + ((rank << k) + bin) * 4, hi_off, min_off, w, f2key(x), a.one);
+      if (i < n) rebin(i);
     }
     __syncwarp();
     cnt = 0;
@@ -1081,8 +1084,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __
     if (g_first + (size_t)u * stride < ngroups) buf[u].load(a.idx, g_first + (size_t)u * stride);
   // every lane of a warp runs the same number of iterations (the warp's first lane decides)
   const size_t g_warp = g_first - lane;
-  uint32_t it = 0;
-  for (size_t gw = g_warp; gw < ngroups; gw += (size_t)DEPTH * stride) {
+  uint32_t it = 0;  // sub-iterations done: outer iteration * DEPTH
+  for (size_t gw = g_warp; gw < ngroups; gw += (size_t)DEPTH * stride, it += DEPTH) {
+    // The matches of DEPTH sub-iterations (8 points each: one byte of mm per sub-iteration) are
+    // appended to the warp's queue with ONE warp scan: some lane matches in nearly every
+    // sub-iteration, so a scan per sub-iteration costs as much as the matching itself.
+    uint32_t mm = 0;
 #pragma unroll
     for (int u = 0; u < DEPTH; ++u) {
       const size_t gwu = gw + (size_t)u * stride;
@@ -1090,7 +1097,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __
       const size_t g = gwu + lane;
       const IdxVec<IDX> cur = buf[u];
       if (g + (size_t)DEPTH * stride < ngroups) buf[u].load(a.idx, g + (size_t)DEPTH * stride);
-      uint32_t mm = 0;  // which of the lane's points match
       if (g < ngroups) {
         uint32_t v[PPL];
         cur.get(v);
@@ -1103,29 +1109,40 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __
             const uint2 rt = __ldg(&a.node_rt[pn]);
             tg = rt.y < a.rank_limit ? rt.x : TARGET_NONE;
           }
-          mm |= (v[j] == tg ? 1u : 0u) << j;
+          mm |= (v[j] == tg ? 1u : 0u) << (8 * u + j);
         }
       }
-      if (__any_sync(0xffffffffu, mm != 0)) {
-        const uint32_t c = __popc(mm);
-        uint32_t incl = c;  // inclusive warp scan of the match counts
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= (uint32_t)d) incl += o;
-        }
-        uint32_t e = cnt + incl - c;
-#pragma unroll
-        for (int j = 0; j < PPL; ++j)
-          if (mm & (1u << j)) q[e++] = (it << 8) | (lane << 3) | j;
-        const uint32_t added = __shfl_sync(0xffffffffu, incl, 31);
-        cnt += added;
-        matched += added;
-        __syncwarp();
-        if (cnt >= REFINE_BATCH) drain();
-      }
-      ++it;
     }
+    if (!__any_sync(0xffffffffu, mm != 0)) continue;
+    const uint32_t c = __popc(mm);
+    uint32_t incl = c;  // inclusive warp scan of the match counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t added = __shfl_sync(0xffffffffu, incl, 31);
+    matched += added;
+    if (cnt + added > (uint32_t)REFINE_QCAP) drain();  // make room (cnt becomes 0)
+    if (added > (uint32_t)REFINE_QCAP) {
+      // more matches in 1024 points than the queue holds (a node concentrated in one bin): every
+      // lane re-bins its own matches directly
+      for (uint32_t m = mm; m; m &= m - 1) {
+        const uint32_t bit = __ffs(m) - 1;
+        const size_t i = (g_first + (size_t)(it + (bit >> 3)) * stride) * PPL + (bit & 7);
+        if (i < n) rebin(i);
+      }
+      __syncwarp();
+      continue;
+    }
+    uint32_t e = cnt + incl - c;
+    for (uint32_t m = mm; m; m &= m - 1) {
+      const uint32_t bit = __ffs(m) - 1;
+      q[e++] = ((it + (bit >> 3)) << 8) | (lane << 3) | (bit & 7);
+    }
+    cnt += added;
+    __syncwarp();
+    if (cnt >= REFINE_BATCH) drain();
   }
   drain();
   if (lane == 0 && matched) atomicAdd(&a.gp->refine_points, matched);

@@ -323,6 +323,30 @@ def test_pass_schedules_do_not_change_results(cb, oracle, opts):
     ctx.close()
 
 
+def test_refinement_with_dense_matches(cb, oracle):
+    """Most points of a node inside the one bin under refinement: the refinement sweep's match queue
+    overflows and lanes re-bin their matches directly; several refinement rounds per level."""
+    rng = np.random.default_rng(41)
+    n = 400_003
+    pts = rng.random((n, 3))
+    tight = rng.random(n) < 0.9
+    pts[tight] = 0.37 + rng.normal(size=(int(tight.sum()), 3)) * 1e-5
+    for wk, tol in (("i64", 0.0), ("f64", 0.01)):
+        w = gen_weights(rng, n, wk)
+        for opts in ({}, {"kmax_a": 3, "kmax_refine": 4}):
+            ctx = cb.Context(0)
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            want, tr = oracle.rcb(pts, w, 8, tol, mode=1, trace=True)
+            got = run_device(cb, pts, w, 8, tol, ctx=ctx)
+            assert np.array_equal(got, want)
+            v = tr.visited.astype(bool)
+            assert np.array_equal(ctx.trace(8)["split_pos"][v], tr.split_pos[v])
+            st = ctx.stats()
+            assert st["refine_sweeps"] > 0 and st["refine_points"] > n // 4
+            ctx.close()
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_rib_against_oracle(cb, oracle, dim):
     rng = np.random.default_rng(dim)
