@@ -952,7 +952,7 @@ fill_hist_kernel(unsigned long long *hist_w, uint32_t *hist_min, uint32_t nb, co
 // ---------------------------------------------------------------------------
 // Sparse sweep: only the points of the one first-pass bin an undecided
 // bisection narrowed down to contribute; every other point costs its idx word
-// and nothing else.  The undecided nodes are ranked (rank_unresolved_kernel) so
+// and nothing else.  The undecided nodes are ranked (rank_unresolved_block, by the walk kernel) so
 // that their histograms are dense: slot = (rank << k) + bin, kept in shared
 // memory like the dense pass.
 // ---------------------------------------------------------------------------
