@@ -532,8 +532,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
 
   size_t ev_used = 0;
   c->event_kind.clear();
-  auto time_begin = [&](int kind) {
-    if (!c->time_sweeps) return;
+  bool timing_open = false;
+  auto time_begin = [&](int kind) {  // option time_sweeps: 1 = dense sweeps, 2 = refinement sweeps too (and print)
+    timing_open = c->time_sweeps > kind;
+    if (!timing_open) return;
     while (c->events.size() < ev_used + 2) {
       cudaEvent_t e;
       CU(cudaEventCreate(&e));
@@ -543,7 +545,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     CU(cudaEventRecord(c->events[ev_used], st));
   };
   auto time_end = [&]() {
-    if (!c->time_sweeps) return;
+    if (!timing_open) return;
     CU(cudaEventRecord(c->events[ev_used + 1], st));
     ev_used += 2;
   };
