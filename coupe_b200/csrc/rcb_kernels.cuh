@@ -59,6 +59,7 @@ struct GlobalParams {
   uint32_t leaf_min;               // smallest non-empty leaf path
   uint32_t walk_ticket;            // blocks of the current walk launch that are done (reset by the last one)
   uint32_t rescale;                // the sampled max |w| gave another fixed-point shift than the true one: redo the root pass
+  uint32_t any_undecided;          // some node of the pass being walked is still undecided (reset by the last block)
   unsigned long long refine_points;  // points the refinement sweeps of the call re-binned (statistics)
   int shift;
 };
@@ -1288,7 +1289,10 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
   const int axis = a.level % a.D, next_axis = (a.level + 1) % a.D;
   const uint32_t heap = ((1u << a.level) - 1) + p;
 
-  if (!a.first && !ns.done && a.node_rt[p].y >= a.rank_limit) return;  // waits for a later pass
+  if (!a.first && !ns.done && a.node_rt[p].y >= a.rank_limit) {  // waits for a later pass
+    if (threadIdx.x == 0) a.gp->any_undecided = 1;
+    return;
+  }
   if (a.first ? !ns.alive : ns.done) {
     if (a.first && threadIdx.x == 0) {  // empty node: rcb_recurse returns at once (:586-588)
       ns.done = 1;
@@ -1459,6 +1463,7 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     if (a.first) ns.sb = t - nb;  // the dense-pass bin the bracket has shrunk to
     a.target[p] = (p << a.k0) + ns.sb;
     a.rtable[p] = make_float4(lo, hi, hi_incl ? 1.f : 0.f, 0.f);
+    a.gp->any_undecided = 1;
     return;
   }
   ns.done = 1;
@@ -1530,6 +1535,18 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
   if (!s_last) return;
   if (threadIdx.x == 0) a.gp->walk_ticket = 0;
   __threadfence();
+  if (__ldcg(&a.gp->any_undecided) == 0) {  // the usual case: every node decided, nothing to rank
+    if (threadIdx.x == 0) {
+      a.gp->unresolved = 0;
+      __threadfence();
+      *a.host_flag = FLAG_VALID | ((unsigned long long)(a.gp->rescale & 1u) << 33) |
+                     ((unsigned long long)a.gp->w_wide << 32);
+      __threadfence_system();
+    }
+    return;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.gp->any_undecided = 0;
   rank_unresolved_block(a.target, 1u << a.level, const_cast<uint2 *>(a.node_rt), a.rtable, a.rfast,
                         a.refine_cap, a.kmax_refine, a.gp, a.host_flag);
 }
