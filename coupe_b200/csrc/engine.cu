@@ -713,7 +713,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   auto enqueue_emit = [&](int klast, const uint32_t *guard) {
     const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
     unsigned long long *out = reinterpret_cast<unsigned long long *>(part_dev);
-    const int out_vec = ((uintptr_t)part_dev % 16) == 0;
+    const int out_vec = ((uintptr_t)part_dev % 32) == 0 ? 2 : ((uintptr_t)part_dev % 16) == 0 ? 1 : 0;
     if (idx16)
       emit_kernel<uint16_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
     else

@@ -1578,7 +1578,11 @@ emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp
       const uint32_t sbword = __float_as_uint(__ldg(&table[p]).w);
       r[j] = (unsigned long long)(2 * p + child_of(v[j], sbword, xp, i0 + j, table_split + p) - off);
     }
-    if (i0 + 4 <= n && out_vec) {
+    if (i0 + 4 <= n && out_vec == 2) {  // 32-byte aligned output: one 256-bit streaming store per thread
+      asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + i0), "l"(r[0]), "l"(r[1]), "l"(r[2]),
+                   "l"(r[3])
+                   : "memory");
+    } else if (i0 + 4 <= n && out_vec) {
       __stcs(reinterpret_cast<ulonglong2 *>(out + i0), make_ulonglong2(r[0], r[1]));
       __stcs(reinterpret_cast<ulonglong2 *>(out + i0) + 1, make_ulonglong2(r[2], r[3]));
     } else {

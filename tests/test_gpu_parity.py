@@ -295,6 +295,24 @@ def test_edge_cases(cb, oracle):
     assert np.array_equal(part.cpu().numpy().astype(np.uint64), oracle.rcb(pts, w[1:].copy(), 7, 0.05))
 
 
+def test_output_alignment_variants(cb, oracle):
+    """emit_kernel stores 32, 16 or 8 bytes at a time depending on the alignment of the caller's id array."""
+    rng = np.random.default_rng(9)
+    n = 100_003
+    pts = rng.random((n, 3))
+    w = rng.integers(1, 9, n).astype(np.int64)
+    want = oracle.rcb(pts, w, 6, 0.05)
+    dev = torch.device("cuda", 0)
+    tp, tw = torch.from_numpy(pts).to(dev), torch.from_numpy(w).to(dev)
+    for off in (0, 1, 2, 3):
+        buf = torch.full((n + 8,), -1, dtype=torch.int64, device=dev)
+        part = buf[off:off + n]
+        cb.Rcb(6, 0.05).partition(part, (tp, tw))
+        assert np.array_equal(part.cpu().numpy().astype(np.uint64), want)
+        assert int(buf[off - 1]) == -1 if off else True
+        assert int(buf[off + n]) == -1
+
+
 @pytest.mark.parametrize("opts", [
     {"force_global": 1},
     {"nb_smem_log2": 8, "kmax_a": 2, "kmax_refine": 2},
