@@ -621,7 +621,9 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
                 tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
                 plan_first(c, level + 1).k, rfast, refine_cap(level, rts_, rtb_), c->kmax_refine,
-                verify_scale ? 1 : 0, c->d_flags + flag_slot(s), make_xchg(s)};
+                verify_scale ? 1 : 0,
+                (unsigned long long)(((n / 4) / ((size_t)sweep_grid * SWEEP_THREADS) + 1) * SWEEP_THREADS * 4 + 4),
+                c->d_flags + flag_slot(s), make_xchg(s)};
     const size_t bytes = ((size_t)2 << k) * 12;
     const uint32_t nodes = 1u << level;
     // the last block to finish ranks the undecided nodes and reports to the host flag
@@ -793,10 +795,12 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->flag_seq = seq;
   CU(cudaMemcpyAsync(c->h_pinned + 2, &gp->refine_points, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_pinned + 5, &gp->nocarry, 4, cudaMemcpyDeviceToHost, st));
   if (use_xchg) CU(cudaMemcpyAsync(c->h_pinned + 1, c->xchg_aux + 1, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
   memcpy(&S.weight_shift, c->h_pinned, 4);
   S.peer_exchange = use_xchg ? 1 : 0;
+  S.carry_free = c->h_pinned[5];
   memcpy(&S.refine_points, c->h_pinned + 2, 8);
   if (use_xchg && c->h_pinned[1] != 0) {
     fprintf(stderr, "coupe_b200: a rank did not deliver its histogram in time (peer-memory exchange)\n");

@@ -60,6 +60,9 @@ struct GlobalParams {
   uint32_t walk_ticket;            // blocks of the current walk launch that are done (reset by the last one)
   uint32_t rescale;                // the sampled max |w| gave another fixed-point shift than the true one: redo the root pass
   uint32_t any_undecided;          // some node of the pass being walked is still undecided (reset by the last block)
+  uint32_t wmax_u32;               // integer weights: largest weight seen by the root sweep (saturating), and
+  uint32_t w_negative;             // ... whether any is negative
+  uint32_t nocarry;                // decided after the root pass: 32-bit block-private sums cannot overflow
   unsigned long long refine_points;  // points the refinement sweeps of the call re-binned (statistics)
   int shift;
 };
@@ -651,6 +654,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   const bool narrow = ROOT && WIN != WIN_CONST && a.w32_out != nullptr;
   bool wide = false;  // some i64 weight does not fit the narrowed i32 column
   double wmax = 0.0;  // root sweep over f64 weights: the true max |w| (verifies the sampled exponent)
+  uint32_t wmaxi = 0;  // root sweep over integer weights: the largest weight (saturating) ...
+  bool wneg = false;   // ... and whether any weight is negative
+  const bool nocarry = !ROOT && WIN == WIN_I32 && a.gp->nocarry != 0;
   const uint32_t kbit = 1u << k;
   // slot = (parent << (k+1)) + child * 2^k + bin; the bin comes out of the float trick below as
   // bits(tf) = 0x4B000000 + bin, so the constant is folded into the child term
@@ -717,6 +723,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     long long w[4];
     cur.w.get(scale, w);
     if (ROOT && WIN == WIN_F64) wmax = fmax(wmax, cur.w.maxabs());
+    if (ROOT && (WIN == WIN_I32 || WIN == WIN_I64)) {  // largest weight: decides the carry-free path of the later sweeps
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        wneg = wneg || w[j] < 0;
+        const unsigned long long u = (unsigned long long)w[j];
+        wmaxi = max(wmaxi, u > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)u);
+      }
+    }
     if (narrow) {
       __stcs(reinterpret_cast<int4 *>(a.w32_out + i0),
              make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
@@ -735,6 +749,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       if (WIN == WIN_CONST) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) reds_add(addr[j], a.one);  // a block sees fewer than 2^32 points
+      } else if (nocarry) {
+        // small non-negative integer weights: (largest weight) x (points this block sweeps) < 2^32, so
+        // the low word alone holds the sum: one fire-and-forget add per point, nothing returns
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reds_add(addr[j], (uint32_t)w[j]);
       } else if (((w[0] | w[1] | w[2] | w[3]) >> 32) == 0) {
         // four non-negative weights below 2^32 (the common case): one returning add each; the carry
         // out of the low word goes to the high word (with 2^30-sized fixed-point weights some lane
@@ -798,6 +817,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       static_cast<IDX *>(a.idx)[i] = (IDX)slot;
       const long long w = load_w1<WIN>(a.w, i, scale);
       if (ROOT && WIN == WIN_F64) wmax = fmax(wmax, fabs(static_cast<const double *>(a.w)[i]));
+      if (ROOT && (WIN == WIN_I32 || WIN == WIN_I64)) {
+        wneg = wneg || w < 0;
+        wmaxi = max(wmaxi, (unsigned long long)w > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w);
+      }
       if (narrow) {
         a.w32_out[i] = (int)w;
         if (WIN == WIN_I64) wide = wide || w != (int)w;
@@ -807,6 +830,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     }
   }
   if (ROOT && WIN == WIN_I64 && wide) a.gp->w_wide = 1;
+  if (ROOT && (WIN == WIN_I32 || WIN == WIN_I64)) {
+    wmaxi = __reduce_max_sync(0xffffffffu, wmaxi);
+    const bool anyneg = __any_sync(0xffffffffu, wneg);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(&a.gp->wmax_u32, wmaxi);
+      if (anyneg) a.gp->w_negative = 1;
+    }
+  }
   if (ROOT && WIN == WIN_F64) {  // bit patterns of non-negative doubles order like unsigned integers
     unsigned long long wb = (unsigned long long)__double_as_longlong(wmax);
 #pragma unroll
@@ -1274,6 +1305,7 @@ struct WalkArgs {
   uint32_t refine_cap;       // histogram slots a refinement pass may use at this level
   int kmax_refine;
   int verify_scale;          // level 0, f64 weights: max |w| was sampled (GlobalParams::rescale)
+  unsigned long long block_points;  // points one block of a dense sweep processes at most (carry-free decision)
   volatile unsigned long long *host_flag;  // mapped host word the pass reports to
   Xchg x;                    // multi-GPU: read the histogram from the exchange buffer (world > 1)
 };
@@ -1372,6 +1404,8 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     hi_incl = 1;
     below_nonempty = 0;
     if (a.level == 0) ns.sum = O::canon((long long)wtree[1]);  // :684, total weight
+    if (a.level == 0 && WT != WT_F64 && !a.w_is_const)
+      a.gp->nocarry = (!a.gp->w_negative && (unsigned long long)a.gp->wmax_u32 * a.block_points < 0xFFFFFFFFull) ? 1u : 0u;
     if (a.level == 0 && WT == WT_F64 && !a.w_is_const && a.verify_scale) {
       // the scale came from a sample of the weights: the true maximum (root sweep) must give the same shift
       const int want = fixed_point_shift(__longlong_as_double((long long)a.gp->maxabs_true_bits), a.gp->n_global);

@@ -44,6 +44,8 @@ typedef struct coupe_b200_stats {
 	uint32_t host_syncs;     /* stream synchronisations inside the call */
 	uint32_t flag_waits;     /* passes whose result the host polled for (mapped host memory) */
 	uint32_t peer_exchange;  /* 1: histograms went through the peer-memory exchange, 0: NCCL / single GPU */
+	uint32_t carry_free;     /* 1: integer weights small enough for 32-bit block-private sums (no carry chain in the sweeps) */
+	uint32_t reserved;
 	uint32_t weight_rescales; /* f64 weights: 1 when the sampled max |w| missed the exponent and the root pass was redone */
 	double   matrix[9];      /* RIB: the obb_to_aabb matrix applied (row-major DxD) */
 	double   dense_sweep_ms; /* option "time_sweeps": summed device time of the dense sweeps */

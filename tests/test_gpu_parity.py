@@ -295,6 +295,21 @@ def test_edge_cases(cb, oracle):
     assert np.array_equal(part.cpu().numpy().astype(np.uint64), oracle.rcb(pts, w[1:].copy(), 7, 0.05))
 
 
+def test_carry_free_path_for_small_integer_weights(cb, oracle):
+    """Integer weights with (largest weight) x (points per block) < 2^32 take the sweeps' carry-free adds;
+    larger or negative ones the two-word path.  Same ids either way."""
+    rng = np.random.default_rng(12)
+    n = 500_003
+    pts = rng.random((n, 2))
+    ctx = cb.Context(0)
+    for w, want_cf in ((rng.integers(1, 100, n).astype(np.int64), 1), (rng.integers(1, 100, n).astype(np.int32), 1),
+                       (rng.integers(0, 2**31 - 1, n).astype(np.int64), 0), (rng.integers(-5, 100, n).astype(np.int32), 0),
+                       (rng.integers(0, 2**40, n).astype(np.int64), 0)):
+        assert np.array_equal(run_device(cb, pts, w, 9, 0.01, ctx=ctx), oracle.rcb(pts, w, 9, 0.01))
+        assert ctx.stats()["carry_free"] == want_cf
+    ctx.close()
+
+
 def test_output_alignment_variants(cb, oracle):
     """emit_kernel stores 32, 16 or 8 bytes at a time depending on the alignment of the caller's id array."""
     rng = np.random.default_rng(9)
