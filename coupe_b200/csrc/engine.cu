@@ -34,6 +34,26 @@ struct CudaFail {
     if (e__ != cudaSuccess) throw CudaFail{e__, #call}; \
   } while (0)
 
+// Programmatic dependent launch: the kernels of the level loop are launched with the
+// "programmatic stream serialization" attribute, so the next kernel's blocks are scheduled while
+// the previous kernel drains; every such kernel starts with griddepcontrol.launch_dependents /
+// griddepcontrol.wait (rcb_kernels.cuh: pdl_enter) and touches global memory only after the wait.
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = [] { const char *e = getenv("COUPE_B200_NO_PDL"); return e && *e && *e != '0'; }();
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  CU(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 struct NcclApi {
   void *handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -234,10 +254,10 @@ size_t sweep_smem_bytes(int level, int rep_log2) {
 template <int WIN, bool ROOT>
 void launch_sweep(bool smem, bool tsm, bool idx16, int grid, size_t bytes, cudaStream_t st,
                   const SweepArgs &a) {
-  if (smem && idx16) sweep_kernel<WIN, true, ROOT, true, uint16_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else if (smem) sweep_kernel<WIN, true, ROOT, true, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else if (tsm) sweep_kernel<WIN, false, ROOT, true, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else sweep_kernel<WIN, false, ROOT, false, uint32_t><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  if (smem && idx16) launch_pdl(sweep_kernel<WIN, true, ROOT, true, uint16_t>, grid, SWEEP_THREADS, bytes, st, a);
+  else if (smem) launch_pdl(sweep_kernel<WIN, true, ROOT, true, uint32_t>, grid, SWEEP_THREADS, bytes, st, a);
+  else if (tsm) launch_pdl(sweep_kernel<WIN, false, ROOT, true, uint32_t>, grid, SWEEP_THREADS, bytes, st, a);
+  else launch_pdl(sweep_kernel<WIN, false, ROOT, false, uint32_t>, grid, SWEEP_THREADS, bytes, st, a);
 }
 
 void launch_sweep_any(int win, bool root, bool smem, bool tsm, bool idx16, int grid, size_t bytes,
@@ -260,9 +280,9 @@ void launch_sweep_any(int win, bool root, bool smem, bool tsm, bool idx16, int g
 
 template <int WIN>
 void launch_refine(bool idx16, bool rts, int grid, size_t bytes, cudaStream_t st, const RefineArgs &a) {
-  if (idx16) sweep_refine_kernel<WIN, uint16_t, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);  // 2^16 idx values: always staged
-  else if (rts) sweep_refine_kernel<WIN, uint32_t, true><<<grid, SWEEP_THREADS, bytes, st>>>(a);
-  else sweep_refine_kernel<WIN, uint32_t, false><<<grid, SWEEP_THREADS, bytes, st>>>(a);
+  if (idx16) launch_pdl(sweep_refine_kernel<WIN, uint16_t, true>, grid, SWEEP_THREADS, bytes, st, a);  // 2^16 idx values: always staged
+  else if (rts) launch_pdl(sweep_refine_kernel<WIN, uint32_t, true>, grid, SWEEP_THREADS, bytes, st, a);
+  else launch_pdl(sweep_refine_kernel<WIN, uint32_t, false>, grid, SWEEP_THREADS, bytes, st, a);
 }
 
 void prepare_funcs(coupe_b200_ctx *c) {
@@ -627,9 +647,9 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const size_t bytes = ((size_t)2 << k) * 12;
     const uint32_t nodes = 1u << level;
     // the last block to finish ranks the undecided nodes and reports to the host flag
-    if (wtype == WT_I32) walk_kernel<WT_I32><<<nodes, WALK_THREADS, bytes, st>>>(wa);
-    else if (wtype == WT_I64) walk_kernel<WT_I64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
-    else walk_kernel<WT_F64><<<nodes, WALK_THREADS, bytes, st>>>(wa);
+    if (wtype == WT_I32) launch_pdl(walk_kernel<WT_I32>, nodes, WALK_THREADS, bytes, st, wa);
+    else if (wtype == WT_I64) launch_pdl(walk_kernel<WT_I64>, nodes, WALK_THREADS, bytes, st, wa);
+    else launch_pdl(walk_kernel<WT_F64>, nodes, WALK_THREADS, bytes, st, wa);
     R.launched(1);
     return s;
   };
@@ -663,7 +683,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.one = 1;
     sa.table_rep_log2 = plan.table_rep_log2;
     if (!plan.smem) {
-      fill_hist_kernel<<<(nb + 255) / 256, 256, 0, st>>>(hist_w, hist_min, nb, guard);
+      launch_pdl(fill_hist_kernel, (nb + 255) / 256, 256, 0, st, hist_w, hist_min, nb, guard);
       R.launched();
     }
     time_begin(0);
@@ -672,8 +692,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     R.launched();
     S.dense_sweeps += 1;
     if (plan.smem) {
-      reduce_partials_kernel<<<(nb + 31) / 32, 256, 0, st>>>(sa.part_w, sa.part_min, sweep_grid, nb,
-                                                             hist_w, hist_min, guard, make_xchg(seq));
+      launch_pdl(reduce_partials_kernel, (nb + 31) / 32, 256, 0, st, sa.part_w, sa.part_min, sweep_grid, nb, hist_w,
+                 hist_min, guard, make_xchg(seq));
       R.launched();
     }
     allreduce_hist(nb);
@@ -699,8 +719,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       default: launch_refine<WIN_CONST>(idx16, rts, sweep_grid, rbytes, st, ra); break;
     }
     time_end();
-    reduce_partials_kernel<<<(nslots + 31) / 32, 256, 0, st>>>(ra.part_w, ra.part_min, sweep_grid,
-                                                               nslots, hist_w, hist_min, nullptr, make_xchg(seq));
+    launch_pdl(reduce_partials_kernel, (nslots + 31) / 32, 256, 0, st, ra.part_w, ra.part_min, sweep_grid, nslots,
+               hist_w, hist_min, (const uint32_t *)nullptr, make_xchg(seq));
     R.launched(2);
     S.refine_sweeps += 1;
     allreduce_hist(nslots);
@@ -717,9 +737,9 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     unsigned long long *out = reinterpret_cast<unsigned long long *>(part_dev);
     const int out_vec = ((uintptr_t)part_dev % 32) == 0 ? 2 : ((uintptr_t)part_dev % 16) == 0 ? 1 : 0;
     if (idx16)
-      emit_kernel<uint16_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+      launch_pdl(emit_kernel<uint16_t>, grid, 512, 0, st, n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
     else
-      emit_kernel<uint32_t><<<grid, 512, 0, st>>>(n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+      launch_pdl(emit_kernel<uint32_t>, grid, 512, 0, st, n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
     R.launched();
   };
 
