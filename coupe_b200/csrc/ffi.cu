@@ -114,9 +114,12 @@ struct StageLane {
 };
 StageLane g_lanes[STAGE_THREADS];
 bool g_lanes_ready = false;
+int g_lanes_device = -1;  // the streams belong to the device of the first call; other devices use plain copies
 
-bool ensure_lanes() {
-  if (g_lanes_ready) return true;
+bool ensure_lanes(int device) {
+  if (g_lanes_ready) return g_lanes_device == device;
+  if (g_lanes_device >= 0) return false;  // an earlier attempt failed half way
+  g_lanes_device = device;
   for (StageLane &l : g_lanes) {
     for (int b = 0; b < 2; ++b) {
       if (cudaHostAlloc(&l.buf[b], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) return false;
@@ -142,7 +145,7 @@ bool staged_copy(void *dev, void *host, size_t bytes, bool to_device, int device
   if (bytes == 0) return true;
   const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   static const bool no_staging = [] { const char *e = getenv("COUPE_B200_NO_STAGING"); return e && *e && *e != '0'; }();
-  if (no_staging || bytes < 4 * STAGE_CHUNK || is_pinned(host) || !ensure_lanes())
+  if (no_staging || bytes < 4 * STAGE_CHUNK || is_pinned(host) || !ensure_lanes(device))
     return cudaMemcpy(to_device ? dev : host, to_device ? host : dev, bytes, kind) == cudaSuccess;
   const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
   const unsigned nt = (unsigned)std::min<size_t>(STAGE_THREADS, nchunks);
