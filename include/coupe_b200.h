@@ -119,7 +119,16 @@ int coupe_b200_last_trace(coupe_b200_ctx *ctx, uint8_t *visited, float *split_po
  * later calls do not allocate. */
 int coupe_b200_reserve(coupe_b200_ctx *ctx, uintptr_t n, uintptr_t dim, uintptr_t iter_count);
 
-/* Tuning knobs for experiments (bench/profiles); safe defaults otherwise. */
+/* Tuning knobs for experiments (bench/profiles); safe defaults otherwise.  Unknown names return
+ * COUPE_ERR_NOT_FOUND.
+ *   kmax_a (1..10, 8)        bisection steps a dense sweep resolves (2^k bins per node)
+ *   kmax_refine (1..10, 10)  ... a refinement sweep
+ *   nb_smem_log2 (6..14, 14) histogram slots a block keeps in shared memory
+ *   force_global (0)         accumulate with L2 atomics instead of shared-memory histograms
+ *   trace (1)                keep the split tree for coupe_b200_last_trace
+ *   time_sweeps (0)          1: CUDA events around the dense sweeps, 2: refinement sweeps too (printed)
+ *   peer_exchange (1)        multi-GPU: histograms over peer memory (0: NCCL all-reduces)
+ *   sample_weights (1)       f64 weights: max |w| from a sample, verified by the root sweep */
 int coupe_b200_set_option(coupe_b200_ctx *ctx, const char *name, int64_t value);
 
 /* Library / build identification string. */
