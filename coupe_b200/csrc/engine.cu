@@ -404,11 +404,6 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->target.ensure(max_nodes * sizeof(uint32_t));
   c->node_rt.ensure(max_nodes * sizeof(uint2));
   c->rfast.ensure(max_nodes * sizeof(float2));
-  // i32 column read by the sweeps below the root: narrowed f64 / i64 weights, or an aligned copy
-  // of caller's i32 weights that are not 16-byte aligned
-  const bool narrow_w = w_dev && (wtype == WT_F64 || (wtype == WT_I64 && L > 1) ||
-                                  (wtype == WT_I32 && L > 1 && ((uintptr_t)w_dev % 16) != 0));
-  if (narrow_w) c->w32.ensure(npad * sizeof(int));
   c->gp.ensure(sizeof(GlobalParams));
   c->mom_partial.ensure((size_t)c->num_sms * 8 * 16 * sizeof(double));
   const size_t tr_n = L > 0 ? ((size_t)1 << L) - 1 : 1;
@@ -443,6 +438,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     any_rank_has_array_weights = h[1] != 0;
   }
   S.n_global = n_global;
+  // i32 column read by the sweeps below the root: narrowed f64 / i64 weights, or an aligned copy
+  // of caller's i32 weights that are not 16-byte aligned.  Decided on the GLOBAL "weights are an
+  // array" fact: a rank with an empty shard must take the same collective steps as the others.
+  const bool narrow_w = any_rank_has_array_weights &&
+                        (wtype == WT_F64 || (wtype == WT_I64 && L > 1) ||
+                         (wtype == WT_I32 && L > 1 && w_dev && ((uintptr_t)w_dev % 16) != 0));
+  if (narrow_w) c->w32.ensure(npad * sizeof(int));
   if (n_global == 0) return COUPE_ERR_OK;  // BoundingBox::from_points -> None (:685-688)
   if (L == 0) {                            // iter_count == 0: every id is 0
     if (n) CU(cudaMemsetAsync(part_dev, 0, n * sizeof(uint64_t), st));

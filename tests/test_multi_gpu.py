@@ -82,6 +82,8 @@ def two_gpus():
     ("i64big", 2, 8, 0.001, False),
     ("const", 2, 7, 0.0, True),
     ("f64outlier", 3, 8, 0.05, False),  # one huge weight on the second rank, outside every sampled run
+    ("i64", 2, 6, 0.05, True),          # array weights and an empty last shard: same collective steps on every rank
+    ("f64", 3, 6, 0.05, True),
 ])
 def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, empty_last, peer):
     rng = np.random.default_rng(11)
