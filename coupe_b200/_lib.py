@@ -39,7 +39,7 @@ class Stats(C.Structure):
                 ("dense_sweeps", C.c_uint32), ("refine_sweeps", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("collectives", C.c_uint32),
                 ("weight_shift", C.c_int32), ("host_syncs", C.c_uint32), ("flag_waits", C.c_uint32),
-                ("peer_exchange", C.c_uint32), ("carry_free", C.c_uint32), ("reserved", C.c_uint32),
+                ("peer_exchange", C.c_uint32), ("carry_free", C.c_uint32), ("weight_wide", C.c_uint32),
                 ("weight_rescales", C.c_uint32), ("matrix", C.c_double * 9), ("dense_sweep_ms", C.c_double),
                 ("refine_sweep_ms", C.c_double), ("refine_points", C.c_uint64)]
 

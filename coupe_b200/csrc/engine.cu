@@ -214,7 +214,7 @@ struct coupe_b200_ctx {
   std::mutex mu;
   // scratch
   Buf xcols, ids, w32, node_rt, rfast, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
-      tsp_a, tsp_b, target, rtable, gp,
+      tsp_a, tsp_b, nsh_a, nsh_b, target, rtable, gp,
       tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
   uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
   volatile unsigned long long *h_flags = nullptr;  // mapped pinned: one word per pass, written by the GPU
@@ -248,7 +248,8 @@ void setup_xchg(coupe_b200_ctx *c);
 // the split positions and the bracket ends.
 size_t sweep_smem_bytes(int level, int rep_log2) {
   const size_t parents = (size_t)1 << (level > 0 ? level - 1 : 0);
-  return HIST_BYTES + (parents << rep_log2) * sizeof(float4) + parents * 2 * sizeof(float);
+  return HIST_BYTES + (parents << rep_log2) * sizeof(float4) + parents * 2 * sizeof(float) +
+         ((((size_t)2 << level) + 15) & ~(size_t)15);  // + the per-node shifts (f64 weights, wide form)
 }
 
 template <int WIN, bool ROOT>
@@ -273,6 +274,7 @@ void launch_sweep_any(int win, bool root, bool smem, bool tsm, bool idx16, int g
     switch (win) {
       case WIN_I32: launch_sweep<WIN_I32, false>(smem, tsm, idx16, grid, bytes, st, a); break;
       case WIN_I64: launch_sweep<WIN_I64, false>(smem, tsm, idx16, grid, bytes, st, a); break;
+      case WIN_F64: launch_sweep<WIN_F64, false>(smem, tsm, idx16, grid, bytes, st, a); break;
       default: launch_sweep<WIN_CONST, false>(smem, tsm, idx16, grid, bytes, st, a); break;
     }
   }
@@ -300,6 +302,7 @@ void prepare_funcs(coupe_b200_ctx *c) {
   SETALL(WIN_CONST, true);
   SETALL(WIN_I32, false);
   SETALL(WIN_I64, false);
+  SETALL(WIN_F64, false);
   SETALL(WIN_CONST, false);
 #define SETREF(win)                                            \
   SETATTR((sweep_refine_kernel<win, uint16_t, true>));         \
@@ -307,6 +310,7 @@ void prepare_funcs(coupe_b200_ctx *c) {
   SETATTR((sweep_refine_kernel<win, uint32_t, false>))
   SETREF(WIN_I32);
   SETREF(WIN_I64);
+  SETREF(WIN_F64);
   SETREF(WIN_CONST);
 #undef SETREF
 #undef SETALL
@@ -340,7 +344,8 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
     p.k = std::max(1, std::min(c->kmax_a, 17 - level));
     p.copies_log2 = 0;
     p.table_rep_log2 = 0;
-    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float));
+    const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float)) +
+                      ((((size_t)2 << level) + 15) & ~(size_t)15);
     p.table_in_smem = tb <= 64 * 1024;
     p.bytes = p.table_in_smem ? tb : 0;
   }
@@ -401,6 +406,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->rtable.ensure(max_nodes * sizeof(float4));
   c->tsp_a.ensure(max_nodes * sizeof(float));
   c->tsp_b.ensure(max_nodes * sizeof(float));
+  c->nsh_a.ensure(max_nodes * 2 * sizeof(short));
+  c->nsh_b.ensure(max_nodes * 2 * sizeof(short));
   c->target.ensure(max_nodes * sizeof(uint32_t));
   c->node_rt.ensure(max_nodes * sizeof(uint2));
   c->rfast.ensure(max_nodes * sizeof(float2));
@@ -508,8 +515,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     R.launched();
     if (c->world > 1) {
       R.allreduce(gp->bbox_keys, 8, ncclUint32, ncclMin);
-      // max |w|: bit patterns of non-negative doubles order like unsigned integers
-      R.allreduce(&gp->maxabs_bits, 1, ncclUint64, ncclMax);
+      // every statistic is kept as a maximum; decided on the GLOBAL "weights are an array" fact (empty shards)
+      if (wtype == WT_F64 && any_rank_has_array_weights) R.allreduce(gp->wstat_sample, WS_N, ncclUint64, ncclMax);
     }
   }
   long long wconst_i = 1;
@@ -525,16 +532,18 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   float4 *tab_cur = c->table_a.as<float4>(), *tab_next = c->table_b.as<float4>();
   float *thi_cur = c->thi_a.as<float>(), *thi_next = c->thi_b.as<float>();
   float *tsp_cur = c->tsp_a.as<float>(), *tsp_next = c->tsp_b.as<float>();
+  short *nsh_cur = c->nsh_a.as<short>(), *nsh_next = c->nsh_b.as<short>();
   float4 *rtable = c->rtable.as<float4>();
   uint32_t *target = c->target.as<uint32_t>();
-  // max |w| of f64 array weights comes from a sample; the root sweep verifies the exponent
-  const bool verify_scale = c->sample_w_opt && wtype == WT_F64 && !w_is_const;
-  auto enqueue_init_root = [&]() {
-    init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, thi_cur, plan_first(c, 0).k, D, wtype,
-                                      w_is_const, wconst_i, wconst_f, n_global);
+  // per-point f64 weights: the fixed-point form and scale come from statistics of a sample of the weights;
+  // the root sweep computes the true ones and the walk of the root asks for another root pass when they differ
+  const bool verify_form = wtype == WT_F64 && !w_is_const;
+  auto enqueue_init_root = [&](int reuse) {
+    init_root_kernel<<<1, 1, 0, st>>>(gp, cur, tab_cur, thi_cur, nsh_cur, plan_first(c, 0).k, D, wtype,
+                                      w_is_const, wconst_i, wconst_f, n_global, reuse);
     R.launched();
   };
-  enqueue_init_root();
+  enqueue_init_root(0);
 
   const size_t ngroups = (n + 3) / 4;
   const int sweep_grid =
@@ -615,7 +624,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   // whether level l needs refinement; its kernels return at once when it does
   // (gp->unresolved != 0) and the pass is enqueued again after the refinement.
   const uint32_t *guard_ptr = &gp->unresolved;
-  uint32_t w_wide = 0, rescale = 0;
+  uint32_t w_wide = 0, rescale = 0, f64_wide = 0;
   uint64_t seq = c->flag_seq;
   auto flag_slot = [&](uint64_t s) { return s % FLAG_SLOTS; };
   auto wait_flag = [&](uint64_t s) -> uint32_t {
@@ -632,6 +641,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     if (v & FLAG_ABORTED) throw CudaFail{cudaErrorUnknown, "waited on an aborted pass"};
     w_wide = (uint32_t)(v >> 32) & 1u;
     rescale = (uint32_t)(v >> 33) & 1u;
+    f64_wide = (uint32_t)(v >> 34) & 1u;
     return (uint32_t)v;
   };
   // walk + rank of one pass; returns the sequence number of its flag
@@ -640,10 +650,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     size_t rtb_;
     const uint64_t s = seq++;
     c->h_flags[flag_slot(s)] = 0;
-    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, target, node_rt, rtable,
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, nsh_next, target, node_rt, rtable,
                 tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
                 plan_first(c, level + 1).k, rfast, refine_cap(level, rts_, rtb_), c->kmax_refine,
-                verify_scale ? 1 : 0,
+                verify_form ? 1 : 0,
                 (unsigned long long)(((n / 4) / ((size_t)sweep_grid * SWEEP_THREADS) + 1) * SWEEP_THREADS * 4 + 4),
                 c->d_flags + flag_slot(s), make_xchg(s)};
     const size_t bytes = ((size_t)2 << k) * 12;
@@ -673,6 +683,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.table = tab_cur;
     sa.table_hi = thi_cur;
     sa.table_split = tsp_cur;
+    sa.nshift = nsh_cur;
     sa.part_w = c->part_w.as<long long>();
     sa.part_min = c->part_min.as<uint32_t>();
     sa.hist_w = hist_w;
@@ -699,7 +710,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       R.launched();
     }
     allreduce_hist(nb);
-    if (level == 0 && verify_scale) R.allreduce(&gp->maxabs_true_bits, 1, ncclUint64, ncclMax);
+    if (level == 0 && verify_form) R.allreduce(gp->wstat_true, WS_N, ncclUint64, ncclMax);
     return enqueue_walk(level, k, k, 1, 0, guard);
   };
   auto enqueue_refine_round = [&](int level, int k0, uint32_t unresolved) {
@@ -713,11 +724,12 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const uint32_t nslots = limit << kr;
     const size_t rbytes = (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
     RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
-                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u, gp};
+                  c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u, gp, nsh_cur};
     time_begin(1);
     switch (win) {
       case WIN_I32: launch_refine<WIN_I32>(idx16, rts, sweep_grid, rbytes, st, ra); break;
       case WIN_I64: launch_refine<WIN_I64>(idx16, rts, sweep_grid, rbytes, st, ra); break;
+      case WIN_F64: launch_refine<WIN_F64>(idx16, rts, sweep_grid, rbytes, st, ra); break;
       default: launch_refine<WIN_CONST>(idx16, rts, sweep_grid, rbytes, st, ra); break;
     }
     time_end();
@@ -733,6 +745,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     std::swap(tab_cur, tab_next);
     std::swap(thi_cur, thi_next);
     std::swap(tsp_cur, tsp_next);
+    std::swap(nsh_cur, nsh_next);
   };
   auto enqueue_emit = [&](int klast, const uint32_t *guard) {
     const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
@@ -750,7 +763,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   for (int level = 0; level < L; ++level) {
     const int k = plan_first(c, level).k;
     // i64 weights: which column the later sweeps read is only known after the root pass
-    const bool can_speculate = !(level == 0 && ((w32 && wtype == WT_I64) || verify_scale));
+    const bool can_speculate = !(level == 0 && ((w32 && wtype == WT_I64) || verify_form));
     advance_level();
     bool speculated = false;
     uint64_t next_pending = 0;
@@ -766,13 +779,14 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       speculated = true;
     }
     uint32_t unresolved = wait_flag(pending);
-    if (level == 0 && rescale) {
-      // the sample missed the exponent of max |w| (an outlier weight): take the true maximum the root
-      // sweep computed and redo the root pass; every rank sees the same flag
+    for (int redo = 0; level == 0 && rescale; ++redo) {
+      // the sample of the weights gave another fixed-point form or scale than all of them do (an
+      // outlier, a negative or a tiny weight outside the sample), or the wide form wants a finer root
+      // shift: the walk left the parameters to use in GlobalParams; redo the root pass with them.
+      // Every rank sees the same flag.
+      if (redo >= 3) return COUPE_ERR_CRASH;  // cannot happen: sample -> true statistics -> finer root shift
       advance_level();  // back to the root's tables
-      CU(cudaMemcpyAsync(&gp->maxabs_bits, &gp->maxabs_true_bits, 8, cudaMemcpyDeviceToDevice, st));
-      CU(cudaMemsetAsync(&gp->rescale, 0, 4, st));
-      enqueue_init_root();
+      enqueue_init_root(1);
       S.dense_sweeps -= 1;
       S.weight_rescales += 1;
       std::swap(win, win_root);  // the root sweep reads the caller's f64 column
@@ -782,7 +796,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       std::swap(wp, wp_root);
       advance_level();
       unresolved = wait_flag(pending);
-      if (rescale) return COUPE_ERR_CRASH;  // cannot happen: the scale now comes from the true maximum
+    }
+    if (level == 0 && verify_form && f64_wide) {  // wide form: the sweeps keep reading the caller's f64 weights
+      win = WIN_F64;
+      wp = w_dev;
     }
     if (level == 0 && w32 && wtype == WT_I64) {
       if (c->world > 1) {  // every rank must take the same path
@@ -817,10 +834,17 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->flag_seq = seq;
   CU(cudaMemcpyAsync(c->h_pinned + 2, &gp->refine_points, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_pinned + 6, &gp->ec, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned + 5, &gp->nocarry, 4, cudaMemcpyDeviceToHost, st));
   if (use_xchg) CU(cudaMemcpyAsync(c->h_pinned + 1, c->xchg_aux + 1, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
-  memcpy(&S.weight_shift, c->h_pinned, 4);
+  {
+    int sh, ec;
+    memcpy(&sh, c->h_pinned, 4);
+    memcpy(&ec, c->h_pinned + 6, 4);
+    S.weight_shift = wtype == WT_F64 ? sh - ec : 0;
+    S.weight_wide = f64_wide;
+  }
   S.peer_exchange = use_xchg ? 1 : 0;
   S.carry_free = c->h_pinned[5];
   memcpy(&S.refine_points, c->h_pinned + 2, 8);
@@ -994,7 +1018,7 @@ void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
     if (c->xchg_aux) cudaFree(c->xchg_aux);
   }
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->node_rt, &c->rfast, &c->tsp_a, &c->tsp_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
+  for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->node_rt, &c->rfast, &c->tsp_a, &c->tsp_b, &c->nsh_a, &c->nsh_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
                  &c->nodes_b, &c->table_a, &c->table_b, &c->thi_a, &c->thi_b, &c->rtable, &c->gp, &c->tr_visited,
                  &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
     b->release();

@@ -23,6 +23,7 @@ namespace cb {
 
 constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
 enum : int { WT_I32 = 0, WT_I64 = 1, WT_F64 = 2, WT_CONST = 3 };
+constexpr int SHIFT_MAX = 1000;  // largest fixed-point shift of normalised f64 weights (2^shift must be a finite double)
 enum : int { SIDE_NONE = 0, SIDE_MIN = 1, SIDE_MAX = 2 };
 constexpr int SWEEP_THREADS = 1024;
 constexpr int WALK_THREADS = 128;
@@ -36,35 +37,47 @@ struct NodeState {
   uint32_t min_above;          // key of the smallest coordinate >= hi, KEY_EMPTY if none
   uint32_t iters;              // candidates evaluated so far
   uint32_t sb;                 // dense-pass bin the bracket shrank to (refined nodes)
+  int shift;                   // f64 weights: `sum` and the node's histograms count multiples of 2^(ec - shift)
   uint8_t alive;               // node holds at least one point
   uint8_t done;                // split decided
   uint8_t prev_side;           // which bracket end the previous candidate became
   uint8_t hi_incl;             // hi is still the box bound (points == hi belong to the bracket)
   uint8_t below_nonempty;      // some point lies left of the bracket
   uint8_t pad[3];
-  uint32_t pad2;
 };
 
 // Device-resident scalars shared by the kernels of one call.
+// Statistics of per-point f64 weights, each kept so that the value wanted is a MAXIMUM (one
+// atomicMax / ncclMax reduces all four): [0] bits of max |w| (bit patterns of non-negative doubles
+// order like unsigned integers), [1] ~bits of the smallest non-zero |w| (0: none), [2] 1 when some
+// weight is negative, [3] 2048 - e with 2^e the largest power of two dividing every non-zero weight
+// (0: none).
+enum : int { WS_MAXABS = 0, WS_MININV = 1, WS_NEG = 2, WS_LSB = 3, WS_N = 4 };
+
 struct GlobalParams {
-  double q;                        // 2^-shift: value of one fixed-point unit
-  double scale;                    // 2^shift
+  double norm;                     // f64 weights: 2^-ec, |w| * norm < 1 for every weight
+  double scale;                    // ... 2^shift of the root pass
   unsigned long long n_global;     // points over all ranks
-  unsigned long long maxabs_bits;  // bit pattern of max |w| (f64 weights): from a SAMPLE of the weights at first
-  unsigned long long maxabs_true_bits;  // ... over all weights, computed by the root sweep while it quantises
+  unsigned long long wstat_sample[WS_N];  // weight statistics over a SAMPLE of the weights (narrow_kernel) ...
+  unsigned long long wstat_true[WS_N];    // ... and over all of them, computed by the root sweep while it quantises
   long long wconst;                // constant weight in accumulator units
   uint32_t bbox_keys[8];           // [0..D) min keys, [4..4+D) inverted max keys
   uint32_t unresolved;             // nodes whose bisection needs another pass
   uint32_t w_wide;                 // some i64 weight does not fit the narrowed i32 column
   uint32_t leaf_min;               // smallest non-empty leaf path
   uint32_t walk_ticket;            // blocks of the current walk launch that are done (reset by the last one)
-  uint32_t rescale;                // the sampled max |w| gave another fixed-point shift than the true one: redo the root pass
+  uint32_t rescale;                // the root pass ran with other fixed-point parameters than the true weight statistics ask for
+                                   // (or the wide form wants a finer root shift): redo it with the ones left here
+  uint32_t wide;                   // f64 weights: 0 narrow form (i32 column, one shift), 1 wide form (64-bit, shift per node)
+  uint32_t per_node;               // wide form: children choose their own shift (no negative weight)
+  uint32_t forced;                 // 0: parameters from the sample, to be verified; 1: from the true statistics; 2: final
+  int ec;                          // exponent of max |w| (clamped): norm = 2^-ec
   uint32_t any_undecided;          // some node of the pass being walked is still undecided (reset by the last block)
   uint32_t wmax_u32;               // integer weights: largest weight seen by the root sweep (saturating), and
   uint32_t w_negative;             // ... whether any is negative
   uint32_t nocarry;                // decided after the root pass: 32-bit block-private sums cannot overflow
   unsigned long long refine_points;  // points the refinement sweeps of the call re-binned (statistics)
-  int shift;
+  int shift;                       // f64 weights: shift of the root pass, normalised weights (value of a unit: 2^(ec - shift))
 };
 
 struct Trace {
@@ -124,8 +137,46 @@ __device__ __forceinline__ void fast_bin_params(float lo, float hi, int k, float
   half_m_eps = __double2float_rd(0.5 - eps);
 }
 
+// Running weight statistics of one thread (GlobalParams::wstat_*).
+struct WStat {
+  unsigned long long v[WS_N];
+  __device__ __forceinline__ void clear() { v[0] = v[1] = v[2] = v[3] = 0; }
+  __device__ __forceinline__ void add(double w) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(w);
+    const unsigned long long a = b & 0x7FFFFFFFFFFFFFFFull;  // bits of |w|
+    if (a == 0) return;                                      // zeros are exact in every form
+    v[WS_MAXABS] = a > v[WS_MAXABS] ? a : v[WS_MAXABS];
+    v[WS_MININV] = ~a > v[WS_MININV] ? ~a : v[WS_MININV];
+    v[WS_NEG] |= b >> 63;
+    // exponent of the lowest set bit: w is a multiple of 2^lsb
+    const int ex = (int)(a >> 52);
+    unsigned long long mant = a & 0xFFFFFFFFFFFFFull;
+    int E = -1074;
+    if (ex) {
+      mant |= 1ull << 52;
+      E = ex - 1075;
+    }
+    const unsigned long long l = (unsigned long long)(2048 - (E + __ffsll((long long)mant) - 1));
+    v[WS_LSB] = l > v[WS_LSB] ? l : v[WS_LSB];
+  }
+  __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+#pragma unroll
+      for (int k = 0; k < WS_N; ++k) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[k], s);
+        v[k] = o > v[k] ? o : v[k];
+      }
+  }
+  __device__ __forceinline__ void commit(unsigned long long *dst) const {
+#pragma unroll
+    for (int k = 0; k < WS_N; ++k)
+      if (v[k]) atomicMax(dst + k, v[k]);
+  }
+};
+
 // ---------------------------------------------------------------------------
-// Prologue: AoS f64 -> SoA f32 (round to nearest even), bounding box, max |w|.
+// Prologue: AoS f64 -> SoA f32 (round to nearest even), bounding box, weight statistics.
 // ---------------------------------------------------------------------------
 struct Mat3 {
   double m[9];
@@ -142,7 +193,8 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
     mn[d] = __int_as_float(0x7f800000);
     mx[d] = __int_as_float(0xff800000);
   }
-  double wmax = 0.0;
+  WStat ws;
+  ws.clear();
   const size_t ngroups = (n + 3) / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
@@ -194,17 +246,18 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
     if (D == 3)
       __stcs(reinterpret_cast<float4 *>(x2 + i0),
              make_float4(o[D - 1][0], o[D - 1][1], o[D - 1][2], o[D - 1][3]));
-    // max |w| only fixes the exponent of the fixed-point scale: with w_sample set, one run of 256
-    // groups in 64 is read here (block-uniform test) and the root sweep, which reads every weight
-    // anyway, verifies the exponent (GlobalParams::rescale)
+    // The weight statistics only choose the fixed-point form and its scale: with w_sample set, one
+    // run of 256 groups in 64 is read here (block-uniform test) and the root sweep, which reads every
+    // weight anyway, computes the true ones; the walk of the root redoes the root pass when they ask
+    // for other parameters (GlobalParams::rescale)
     if (wf64 && (!w_sample || ((g >> 8) & 63) == 0)) {
       if (full && w_aligned) {
         const double2 a = __ldcs(reinterpret_cast<const double2 *>(wf64 + i0));
         const double2 b = __ldcs(reinterpret_cast<const double2 *>(wf64 + i0) + 1);
-        wmax = fmax(wmax, fmax(fmax(fabs(a.x), fabs(a.y)), fmax(fabs(b.x), fabs(b.y))));
+        ws.add(a.x); ws.add(a.y); ws.add(b.x); ws.add(b.y);
       } else {
         for (int j = 0; j < 4; ++j)
-          if (i0 + j < n) wmax = fmax(wmax, fabs(wf64[i0 + j]));
+          if (i0 + j < n) ws.add(wf64[i0 + j]);
       }
     }
   }
@@ -215,7 +268,6 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
     kmin[d] = f2key(mn[d]);
     kmax[d] = ~f2key(mx[d]);
   }
-  unsigned long long wb = (unsigned long long)__double_as_longlong(wmax);
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
 #pragma unroll
@@ -223,11 +275,10 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
       kmin[d] = min(kmin[d], __shfl_xor_sync(0xffffffffu, kmin[d], s));
       kmax[d] = min(kmax[d], __shfl_xor_sync(0xffffffffu, kmax[d], s));
     }
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, wb, s);
-    wb = o > wb ? o : wb;
   }
+  if (wf64) ws.warp_reduce();
   __shared__ uint32_t s_k[8][8];
-  __shared__ unsigned long long s_w[8];
+  __shared__ unsigned long long s_w[8][WS_N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {
 #pragma unroll
@@ -235,7 +286,8 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
       s_k[warp][d] = kmin[d];
       s_k[warp][4 + d] = kmax[d];
     }
-    s_w[warp] = wb;
+#pragma unroll
+    for (int k = 0; k < WS_N; ++k) s_w[warp][k] = ws.v[k];
   }
   __syncthreads();
   if (threadIdx.x < 8) {
@@ -246,42 +298,98 @@ narrow_kernel(const double *__restrict__ pts, size_t n, float *__restrict__ x0,
       atomicMin(&gp->bbox_keys[slot], v);
     }
   }
-  if (threadIdx.x == 32 && wf64) {
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + WS_N && wf64) {
+    const int k = threadIdx.x - 32;
     unsigned long long v = 0;
-    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = s_w[wv] > v ? s_w[wv] : v;
-    atomicMax(&gp->maxabs_bits, v);
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = s_w[wv][k] > v ? s_w[wv][k] : v;
+    if (v) atomicMax(&gp->wstat_sample[k], v);
   }
 }
 
-// Fixed-point shift for f64 weights: min(31 - e, 62 - e - nbits), max|w| < 2^e, n <= 2^nbits.
-__device__ inline int fixed_point_shift(double maxabs, unsigned long long n_global) {
-  if (!(maxabs > 0.0 && maxabs <= 1.7976931348623157e308)) return 0;
-  int e;
-  frexp(maxabs, &e);
+// ---------------------------------------------------------------------------
+// f64 weights are accumulated as exact integer sums of quantised weights (the result then does not
+// depend on thread, block or GPU count; the reference's own f64 sums depend on rayon's schedule).
+// Weights are first normalised, w' = w * 2^-ec with |w| < 2^ec for every weight, then
+//   narrow form: q = rn(w' * 2^s) as i32, ONE s = min(31, 62 - nbits) for n <= 2^nbits points,
+//                kept as a 4-byte column that the sweeps below the root read;
+//   wide form:   q = rn(w' * 2^s_node) as i64, s_node chosen per tree node so that the node's own
+//                weight is in [2^59, 2^61) units; the sweeps read the caller's f64 column.
+// The narrow form is used when it is provably within 2^-30 relative of the real sums: no negative
+// weight, and every weight either a multiple of 2^-s (exact) or at least 2^(29-s) (its rounding
+// error, at most 2^-(s+1), is then at most 2^-30 of the weight).  In the wide form a partial sum
+// of a node with m points is within m * 2^-60 of the node's weight whatever the dynamic range.
+// With a negative weight somewhere the wide form keeps the root's shift at every node.
+// ---------------------------------------------------------------------------
+struct WeightForm {
+  int ec, shift;
+  uint32_t wide, per_node;
+};
+__host__ __device__ inline int ceil_log2_u64(unsigned long long n) {
   int nbits = 0;
-  while (nbits < 63 && (1ull << nbits) < n_global) ++nbits;
-  return max(-1000, min(1000, min(31 - e, 62 - e - nbits)));
+  while (nbits < 63 && (1ull << nbits) < n) ++nbits;
+  return nbits;
+}
+__device__ inline WeightForm weight_form(const unsigned long long *st, unsigned long long n_global) {
+  WeightForm f;
+  const double maxabs = __longlong_as_double((long long)st[WS_MAXABS]);
+  f.ec = 0;
+  if (maxabs > 0.0 && maxabs <= 1.7976931348623157e308) {
+    frexp(maxabs, &f.ec);
+    f.ec = max(f.ec, -1021);  // 2^-ec must be a finite double
+  }
+  const int nbits = ceil_log2_u64(n_global);
+  const int sn = min(31, 62 - nbits);
+  const bool neg = st[WS_NEG] != 0, any = st[WS_MININV] != 0;
+  const double wmin = __longlong_as_double((long long)~st[WS_MININV]);
+  const int lsb = 2048 - (int)st[WS_LSB];
+  const bool narrow_ok = !neg && (!any || lsb + (sn - f.ec) >= 0 || wmin >= ldexp(1.0, 29 - (sn - f.ec)));
+  f.wide = narrow_ok ? 0u : 1u;
+  f.per_node = (!narrow_ok && !neg) ? 1u : 0u;
+  f.shift = narrow_ok ? sn : 62 - nbits;
+  return f;
+}
+__device__ __forceinline__ double pow2_f64(int e) {  // 2^e, -1022 <= e <= 1023
+  return __hiloint2double((1023 + e) << 20, 0);
+}
+// shift a child node adds to its parent's, from its weight in the parent's units (wide form)
+__device__ inline int child_shift_gain(long long sum, int parent_shift) {
+  if (sum <= 0) return 0;
+  return max(0, min(60 - (64 - __clzll(sum)), SHIFT_MAX - parent_shift));
 }
 
 // ---------------------------------------------------------------------------
-// Root set-up once the (all-reduced) bounding box and max |w| are known.
+// Root set-up once the (all-reduced) bounding box and the sampled weight statistics are known.
+// reuse != 0: keep the weight form the walk of the previous root pass left in GlobalParams.
 // ---------------------------------------------------------------------------
 __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *table0,
-                                 float *table0_hi, int k0, int D, int wtype, int w_is_const,
+                                 float *table0_hi, short *nshift0, int k0, int D, int wtype, int w_is_const,
                                  long long wconst_i, double wconst_f,
-                                 unsigned long long n_global) {
+                                 unsigned long long n_global, int reuse) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   gp->n_global = n_global;
-  // fixed-point shift for f64 weights: min(31 - e, 62 - e - nbits), max|w| < 2^e, n <= 2^nbits
-  int shift = 0;
-  if (wtype == WT_F64)
-    shift = fixed_point_shift(w_is_const ? fabs(wconst_f) : __longlong_as_double((long long)gp->maxabs_bits),
-                              n_global);
-  gp->shift = shift;
-  gp->scale = ldexp(1.0, shift);
-  gp->q = ldexp(1.0, -shift);
+  if (!reuse) {
+    WeightForm f{0, 0, 0u, 0u};
+    if (wtype == WT_F64) {
+      unsigned long long st[WS_N] = {0, 0, 0, 0};
+      if (w_is_const) {  // one factor common to every sum: the narrow form loses nothing
+        st[WS_MAXABS] = (unsigned long long)__double_as_longlong(fabs(wconst_f));
+      } else {
+        for (int k = 0; k < WS_N; ++k) st[k] = gp->wstat_sample[k];
+      }
+      f = weight_form(st, n_global);
+      if (w_is_const) f.wide = f.per_node = 0, f.shift = min(31, 62 - ceil_log2_u64(n_global));
+    }
+    gp->ec = f.ec;
+    gp->shift = f.shift;
+    gp->wide = f.wide;
+    gp->per_node = f.per_node;
+    gp->forced = 0;
+  }
+  gp->rescale = 0;
+  gp->norm = ldexp(1.0, -gp->ec);
+  gp->scale = ldexp(1.0, gp->shift);
   long long wc = 1;
-  if (w_is_const) wc = wtype == WT_F64 ? (long long)__double2int_rn(wconst_f * gp->scale) : wconst_i;
+  if (w_is_const) wc = wtype == WT_F64 ? (long long)__double2int_rn(__dmul_rn(__dmul_rn(wconst_f, gp->norm), gp->scale)) : wconst_i;
   gp->wconst = wc;
   gp->unresolved = 0;
   gp->leaf_min = 0xFFFFFFFFu;
@@ -297,7 +405,7 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   ns.min_above = KEY_EMPTY;
   ns.iters = 0;
   ns.sb = 0;
-  ns.pad2 = 0;
+  ns.shift = gp->shift;
   ns.alive = n_global > 0;
   ns.done = 0;
   ns.prev_side = SIDE_NONE;
@@ -305,6 +413,7 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
   ns.below_nonempty = 0;
   ns.pad[0] = ns.pad[1] = ns.pad[2] = 0;
   *root = ns;
+  nshift0[0] = (short)gp->shift;
   float inv, hme;
   fast_bin_params(ns.box_lo[0], ns.box_hi[0], k0, inv, hme);
   table0[0] = make_float4(ns.box_lo[0], inv, hme, 0.f);
@@ -318,18 +427,19 @@ __global__ void init_root_kernel(GlobalParams *gp, NodeState *root, float4 *tabl
 // ---------------------------------------------------------------------------
 enum : int { WIN_I32 = 0, WIN_I64 = 1, WIN_F64 = 2, WIN_CONST = 3 };
 
-// f64 weight -> fixed point: round to nearest even, saturating to the i32 range
-// (only a weight within 2^-32 (relative) below a power of two can saturate).
-__device__ __forceinline__ int quantise_f64(double w, double scale) {
-  return __double2int_rn(__dmul_rn(w, scale));
+// f64 weight -> fixed point: (w * 2^-ec) * 2^shift rounded to nearest even; the narrow form saturates
+// to the i32 range (only a weight within 2^-32 (relative) below a power of two can saturate).
+__device__ __forceinline__ long long quantise_f64(double w, double norm, double scale, bool wide) {
+  const double t = __dmul_rn(__dmul_rn(w, norm), scale);
+  return wide ? __double2ll_rn(t) : (long long)__double2int_rn(t);
 }
 
+// One weight of the caller's integer formats (f64 weights go through quantise_f64).
 template <int WIN>
-__device__ __forceinline__ long long load_w1(const void *__restrict__ w, size_t i, double scale) {
-  if (WIN == WIN_CONST) return 1;
+__device__ __forceinline__ long long load_w1(const void *__restrict__ w, size_t i) {
   if (WIN == WIN_I32) return (long long)__ldcs(static_cast<const int *>(w) + i);
   if (WIN == WIN_I64) return __ldcs(static_cast<const long long *>(w) + i);
-  return (long long)quantise_f64(__ldcs(static_cast<const double *>(w) + i), scale);
+  return 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -364,6 +474,7 @@ struct SweepArgs {
   const float4 *table;       // per parent: {bracket lo, 2^k / width, 0.5 - eps, split-bin word}
   const float *table_hi;     // per parent: bracket hi (exact descend only)
   const float *table_split;  // per parent: split position (refined parents only)
+  const short *nshift;       // per node of this level: fixed-point shift (f64 weights, wide form)
   long long *part_w;         // SMEM mode: per-block partial histograms [grid][nb]
   uint32_t *part_min;
   unsigned long long *hist_w;  // GLOBAL mode: histogram accumulated with L2 atomics
@@ -476,8 +587,8 @@ struct RawW4 {};
 template <>
 struct RawW4<WIN_CONST> {
   __device__ __forceinline__ void load(const void *, size_t, bool) {}
-  __device__ __forceinline__ void get(double, long long (&o)[4]) const { o[0] = o[1] = o[2] = o[3] = 1; }
-  __device__ __forceinline__ double maxabs() const { return 0.0; }
+  __device__ __forceinline__ void get(long long (&o)[4]) const { o[0] = o[1] = o[2] = o[3] = 1; }
+  __device__ __forceinline__ void raw(double (&)[4]) const {}
 };
 template <>
 struct RawW4<WIN_I32> {
@@ -487,10 +598,10 @@ struct RawW4<WIN_I32> {
     if (vec) v = __ldcs(reinterpret_cast<const int4 *>(p));
     else v = make_int4(__ldcs(p), __ldcs(p + 1), __ldcs(p + 2), __ldcs(p + 3));
   }
-  __device__ __forceinline__ void get(double, long long (&o)[4]) const {
+  __device__ __forceinline__ void get(long long (&o)[4]) const {
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
   }
-  __device__ __forceinline__ double maxabs() const { return 0.0; }
+  __device__ __forceinline__ void raw(double (&)[4]) const {}
 };
 template <>
 struct RawW4<WIN_I64> {
@@ -505,10 +616,10 @@ struct RawW4<WIN_I64> {
       b = make_longlong2(__ldcs(p + 2), __ldcs(p + 3));
     }
   }
-  __device__ __forceinline__ void get(double, long long (&o)[4]) const {
+  __device__ __forceinline__ void get(long long (&o)[4]) const {
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
   }
-  __device__ __forceinline__ double maxabs() const { return 0.0; }
+  __device__ __forceinline__ void raw(double (&)[4]) const {}
 };
 template <>
 struct RawW4<WIN_F64> {
@@ -523,12 +634,9 @@ struct RawW4<WIN_F64> {
       b = make_double2(__ldcs(p + 2), __ldcs(p + 3));
     }
   }
-  __device__ __forceinline__ void get(double scale, long long (&o)[4]) const {
-    o[0] = quantise_f64(a.x, scale); o[1] = quantise_f64(a.y, scale);
-    o[2] = quantise_f64(b.x, scale); o[3] = quantise_f64(b.y, scale);
-  }
-  __device__ __forceinline__ double maxabs() const {
-    return fmax(fmax(fabs(a.x), fabs(a.y)), fmax(fabs(b.x), fabs(b.y)));
+  __device__ __forceinline__ void get(long long (&)[4]) const {}
+  __device__ __forceinline__ void raw(double (&o)[4]) const {  // quantised by the sweep (quantise_f64)
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
   }
 };
 
@@ -639,6 +747,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   const uint32_t rep_lane = threadIdx.x & ((1u << rlog) - 1);
   float *s_split = reinterpret_cast<float *>(s_table + (TSM ? ((size_t)nparents << rlog) : 0));
   float *s_thi = s_split + (TSM ? nparents : 0);
+  short *s_nshift = reinterpret_cast<short *>(s_thi + (TSM ? nparents : 0));  // [nodes of this level], wide f64 only
+  constexpr bool WIDE_LEVEL = !ROOT && WIN == WIN_F64;  // below the root f64 weights are read only in the wide form
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i + 1 <= nwords; i += blockDim.x) {  // (i < nwords; written so for nwords == 0)
       s_lo[i] = 0;
@@ -655,17 +765,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       s_split[i] = a.table_split[i];
       s_thi[i] = a.table_hi[i];
     }
+    if (WIDE_LEVEL)
+      for (int i = threadIdx.x; i < (1 << level); i += blockDim.x) s_nshift[i] = a.nshift[i];
   }
   __syncthreads();
-  const double scale = (WIN == WIN_F64) ? a.gp->scale : 1.0;
+  const double norm = (WIN == WIN_F64) ? a.gp->norm : 1.0;
+  const double scale = (ROOT && WIN == WIN_F64) ? a.gp->scale : 1.0;
+  const bool wide_root = ROOT && WIN == WIN_F64 && a.gp->wide != 0;
   // address of this lane's copy of slot 0; slot s sits slot_stride bytes * s further
   const uint32_t lo_base = smem_addr(s_lo) + (SMEM ? (threadIdx.x & ((1u << clog) - 1)) * 4 : 0);
   const uint32_t slot_stride = 4u << clog;
   // below the root an i32 column is always 16-byte aligned (the caller's own when it is, else the engine's copy)
-  const bool vec = (ROOT || WIN == WIN_I64) ? a.w_vec != 0 : true;
-  const bool narrow = ROOT && WIN != WIN_CONST && a.w32_out != nullptr;
+  const bool vec = (ROOT || WIN == WIN_I64 || WIN == WIN_F64) ? a.w_vec != 0 : true;
+  const bool narrow = ROOT && WIN != WIN_CONST && a.w32_out != nullptr && !wide_root;
   bool wide = false;  // some i64 weight does not fit the narrowed i32 column
-  double wmax = 0.0;  // root sweep over f64 weights: the true max |w| (verifies the sampled exponent)
+  WStat ws;           // root sweep over f64 weights: the true weight statistics (verify the sampled ones)
+  ws.clear();
   uint32_t wmaxi = 0;  // root sweep over integer weights: the largest weight (saturating) ...
   bool wneg = false;   // ... and whether any weight is negative
   const bool nocarry = !ROOT && WIN == WIN_I32 && a.gp->nocarry != 0;
@@ -733,8 +848,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
     for (int j = 0; j < 4; ++j) slot[j] += pk[j] + sel[j];
     Idx4<IDX>::store(a.idx, i0, slot);
     long long w[4];
-    cur.w.get(scale, w);
-    if (ROOT && WIN == WIN_F64) wmax = fmax(wmax, cur.w.maxabs());
+    cur.w.get(w);
+    if (WIN == WIN_F64) {
+      double r[4];
+      cur.w.raw(r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ROOT) {
+          w[j] = quantise_f64(r[j], norm, scale, wide_root);
+          ws.add(r[j]);
+        } else {  // the node's own shift
+          const uint32_t node = slot[j] >> k;
+          const int sh = TSM ? s_nshift[node] : __ldg(a.nshift + node);
+          w[j] = quantise_f64(r[j], norm, pow2_f64(sh), true);
+        }
+      }
+    }
     if (ROOT && (WIN == WIN_I32 || WIN == WIN_I64)) {  // largest weight: decides the carry-free path of the later sweeps
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -784,12 +913,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
               ::"r"(old[j]), "r"((uint32_t)w[j]), "r"(addr[j]), "n"(HIST_HI_OFF), "r"(a.one)
               : "memory");
       } else {
+        // any 64-bit weights (the wide form of f64 weights, large or negative integers): the four
+        // returning adds of the low words are in flight together, then the high words take their
+        // part of the weight plus the carry
+        uint32_t old[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) old[j] = atoms_add(addr[j], (uint32_t)w[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t wlo = (uint32_t)w[j];
-          const uint32_t old = atoms_add(addr[j], wlo);
           int hinc = (int)(w[j] >> 32);
-          if (old > ~wlo) ++hinc;
+          if (old[j] > ~(uint32_t)w[j]) ++hinc;
           if (hinc != 0) reds_add(addr[j] + HIST_HI_OFF, (uint32_t)hinc);
         }
       }
@@ -827,8 +960,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       const float x = a.x[i];
       const uint32_t slot = slot_exact(a, pv, x, i, ROOT);
       static_cast<IDX *>(a.idx)[i] = (IDX)slot;
-      const long long w = load_w1<WIN>(a.w, i, scale);
-      if (ROOT && WIN == WIN_F64) wmax = fmax(wmax, fabs(static_cast<const double *>(a.w)[i]));
+      long long w = load_w1<WIN>(a.w, i);
+      if (WIN == WIN_F64) {
+        const double r = static_cast<const double *>(a.w)[i];
+        if (ROOT) ws.add(r);
+        w = ROOT ? quantise_f64(r, norm, scale, wide_root)
+                 : quantise_f64(r, norm, pow2_f64(__ldg(a.nshift + (slot >> k))), true);
+      }
       if (ROOT && (WIN == WIN_I32 || WIN == WIN_I64)) {
         wneg = wneg || w < 0;
         wmaxi = max(wmaxi, (unsigned long long)w > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w);
@@ -850,14 +988,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       if (anyneg) a.gp->w_negative = 1;
     }
   }
-  if (ROOT && WIN == WIN_F64) {  // bit patterns of non-negative doubles order like unsigned integers
-    unsigned long long wb = (unsigned long long)__double_as_longlong(wmax);
-#pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, wb, sh);
-      wb = o > wb ? o : wb;
-    }
-    if ((threadIdx.x & 31) == 0) atomicMax(&a.gp->maxabs_true_bits, wb);
+  if (ROOT && WIN == WIN_F64) {
+    ws.warp_reduce();
+    if ((threadIdx.x & 31) == 0) ws.commit(a.gp->wstat_true);
   }
   if (SMEM) {
     __syncthreads();
@@ -1018,6 +1151,7 @@ struct RefineArgs {
   int rt_in_smem;
   uint32_t one;            // 1, from the host (see SweepArgs::one)
   GlobalParams *gp;
+  const short *nshift;     // per node: fixed-point shift (f64 weights in the wide form: WIN_F64)
 };
 
 constexpr int REFINE_BATCH = 64;                   // matches a warp lets build up before it drains them
@@ -1091,12 +1225,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __
   uint32_t cnt = 0;  // warp-uniform
   unsigned long long matched = 0;
   const IDX *idx = static_cast<const IDX *>(a.idx);
+  const double wnorm = WIN == WIN_F64 ? a.gp->norm : 1.0;
 
   // One matched point: bracket test, fine bin, ranked shared-memory histogram.
   auto rebin = [&](size_t i) {
     const uint32_t p = ((uint32_t)idx[i] >> k0) & (nodes - 1);
     const float x = __ldg(a.x + i);
-    const long long w = load_w1<WIN>(a.w, i, 1.0);  // issued with the coordinate, not after the bracket test
+    long long w = load_w1<WIN>(a.w, i);  // issued with the coordinate, not after the bracket test
+    if (WIN == WIN_F64)
+      w = quantise_f64(__ldg(static_cast<const double *>(a.w) + i), wnorm, pow2_f64(__ldg(a.nshift + p)), true);
     const float4 r = __ldg(&a.rtable[p]);
     const uint32_t rank = __ldg(&a.node_rt[p]).y;
     const float2 f = __ldg(&a.rfast[p]);
@@ -1258,7 +1395,8 @@ __device__ void rank_unresolved_block(const uint32_t *target, uint32_t nodes, ui
   if (threadIdx.x == 0) {  // the host polls this word (mapped pinned memory) instead of synchronising
     gp->unresolved = unresolved;
     __threadfence();
-    *host_flag = FLAG_VALID | ((unsigned long long)(gp->rescale & 1u) << 33) | ((unsigned long long)gp->w_wide << 32) | unresolved;
+    *host_flag = FLAG_VALID | ((unsigned long long)(gp->wide & 1u) << 34) | ((unsigned long long)(gp->rescale & 1u) << 33) |
+                 ((unsigned long long)gp->w_wide << 32) | unresolved;
     __threadfence_system();
   }
 }
@@ -1272,29 +1410,29 @@ struct WOps;
 template <>
 struct WOps<WT_I32> {  // i32 weights wrap in the reference's release build
   __device__ static long long canon(long long v) { return (long long)(int)v; }
-  __device__ static double f64(long long v, double) { return (double)(int)v; }
+  __device__ static double f64(long long v, int) { return (double)(int)v; }
   __device__ static long long sub(long long a, long long b) {
     return (long long)(int)((unsigned)a - (unsigned)b);
   }
-  __device__ static bool lt(long long a, long long b, double) { return (int)a < (int)b; }
+  __device__ static bool lt(long long a, long long b, int) { return (int)a < (int)b; }
 };
 template <>
 struct WOps<WT_I64> {
   __device__ static long long canon(long long v) { return v; }
-  __device__ static double f64(long long v, double) { return (double)v; }
+  __device__ static double f64(long long v, int) { return (double)v; }
   __device__ static long long sub(long long a, long long b) {
     return (long long)((unsigned long long)a - (unsigned long long)b);
   }
-  __device__ static bool lt(long long a, long long b, double) { return a < b; }
+  __device__ static bool lt(long long a, long long b, int) { return a < b; }
 };
 template <>
-struct WOps<WT_F64> {  // fixed point: value = v * q
+struct WOps<WT_F64> {  // fixed point: value = v * 2^e2, e2 = ec - (shift of the node)
   __device__ static long long canon(long long v) { return v; }
-  __device__ static double f64(long long v, double q) { return __dmul_rn((double)v, q); }
+  __device__ static double f64(long long v, int e2) { return ldexp((double)v, e2); }
   __device__ static long long sub(long long a, long long b) {
     return (long long)((unsigned long long)a - (unsigned long long)b);
   }
-  __device__ static bool lt(long long a, long long b, double q) { return f64(a, q) < f64(b, q); }
+  __device__ static bool lt(long long a, long long b, int e2) { return f64(a, e2) < f64(b, e2); }
 };
 
 struct WalkArgs {
@@ -1306,6 +1444,7 @@ struct WalkArgs {
   float4 *table_next;        // per node: {lo, 2^k/width, 0.5-eps on the next axis, split-bin word}
   float *table_next_hi;      // per node: hi on the next axis
   float *table_next_split;   // per node: split position on this axis
+  short *nshift_next;        // per child node: fixed-point shift (f64 weights)
   uint32_t *target;          // per node: idx value under refinement
   const uint2 *node_rt;      // per node: {target, rank} of the refinement pass being walked
   float4 *rtable;            // per node: refinement bracket
@@ -1319,7 +1458,7 @@ struct WalkArgs {
   float2 *rfast;             // per node: fast binning parameters of the next refinement pass
   uint32_t refine_cap;       // histogram slots a refinement pass may use at this level
   int kmax_refine;
-  int verify_scale;          // level 0, f64 weights: max |w| was sampled (GlobalParams::rescale)
+  int verify_form;           // level 0, per-point f64 weights: check the weight form against the true statistics (GlobalParams::rescale)
   unsigned long long block_points;  // points one block of a dense sweep processes at most (carry-free decision)
   volatile unsigned long long *host_flag;  // mapped host word the pass reports to
   Xchg x;                    // multi-GPU: read the histogram from the exchange buffer (world > 1)
@@ -1350,6 +1489,7 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
       if (!a.last_level) {
         a.next[2 * p].alive = 0;
         a.next[2 * p + 1].alive = 0;
+        a.nshift_next[2 * p] = a.nshift_next[2 * p + 1] = 0;
       }
     }
     return;
@@ -1404,7 +1544,6 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
   if (threadIdx.x != 0) return;
 
   using O = WOps<WT>;
-  const double q = a.gp->q;
   float lo, hi;
   long long w_below;
   uint32_t min_above, iters;
@@ -1421,10 +1560,40 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     if (a.level == 0) ns.sum = O::canon((long long)wtree[1]);  // :684, total weight
     if (a.level == 0 && WT != WT_F64 && !a.w_is_const)
       a.gp->nocarry = (!a.gp->w_negative && (unsigned long long)a.gp->wmax_u32 * a.block_points < 0xFFFFFFFFull) ? 1u : 0u;
-    if (a.level == 0 && WT == WT_F64 && !a.w_is_const && a.verify_scale) {
-      // the scale came from a sample of the weights: the true maximum (root sweep) must give the same shift
-      const int want = fixed_point_shift(__longlong_as_double((long long)a.gp->maxabs_true_bits), a.gp->n_global);
-      if (want != a.gp->shift) a.gp->rescale = 1;
+    if (a.level == 0 && WT == WT_F64 && a.verify_form) {
+      GlobalParams *gp = a.gp;
+      if (gp->forced == 0) {
+        // the form and scale came from a sample of the weights: the statistics of ALL weights (root
+        // sweep) must ask for the same, else the root pass is redone with what they ask for
+        const WeightForm f = weight_form(gp->wstat_true, gp->n_global);
+        gp->forced = 1;
+        if (f.ec != gp->ec || f.shift != gp->shift || f.wide != gp->wide || f.per_node != gp->per_node) {
+          gp->ec = f.ec;
+          gp->shift = f.shift;
+          gp->wide = f.wide;
+          gp->per_node = f.per_node;
+          gp->rescale = 1;
+        }
+      }
+      if (!gp->rescale && gp->forced == 1 && gp->per_node) {
+        // wide form: the root pass ran with the coarse shift that cannot overflow.  When that leaves
+        // the total below 2^(nbits+31) units (worst-case rounding n/2 units: above 2^-31 relative) the
+        // root is quantised again with its total in [2^59, 2^61)
+        gp->forced = 2;
+        const long long total = ns.sum;
+        if (total > 0 && 64 - __clzll(total) < ceil_log2_u64(gp->n_global) + 31) {
+          const int d = child_shift_gain(total, gp->shift);
+          if (d > 0) {
+            gp->shift += d;
+            gp->rescale = 1;
+          }
+        }
+      }
+      if (gp->rescale) {  // this pass is void: the host redoes it (init_root_kernel with reuse)
+        ns.done = 0;
+        a.target[p] = TARGET_NONE;
+        return;
+      }
     }
   } else {
     lo = ns.lo; hi = ns.hi;
@@ -1436,6 +1605,7 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     below_nonempty = ns.below_nonempty;
   }
   const long long sum = ns.sum;
+  const int q = WT == WT_F64 ? a.gp->ec - ns.shift : 0;  // exponent of one accumulator unit
   const double ideal = O::f64(sum, q) / 2.0;  // :548
 
   bool finished = false;
@@ -1541,13 +1711,24 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     cr.box_lo[axis] = split_pos;
     cl.sum = weight_left;
     cr.sum = O::sub(sum, weight_left);
+    cl.shift = cr.shift = ns.shift;
+    if (WT == WT_F64 && a.gp->per_node) {
+      // wide form: a child raises the shift until its own weight is in [2^59, 2^60) units; its
+      // points are quantised afresh from the caller's f64 weights by the next level's sweep
+      const int dl = child_shift_gain(cl.sum, ns.shift), dr = child_shift_gain(cr.sum, ns.shift);
+      cl.shift += dl;
+      cl.sum <<= dl;
+      cr.shift += dr;
+      cr.sum <<= dr;
+    }
+    a.nshift_next[2 * p] = (short)cl.shift;
+    a.nshift_next[2 * p + 1] = (short)cr.shift;
     cl.w_below = cr.w_below = 0;
     cl.lo = cr.lo = 0.f;
     cl.hi = cr.hi = 0.f;
     cl.min_above = cr.min_above = KEY_EMPTY;
     cl.iters = cr.iters = 0;
     cl.sb = cr.sb = 0;
-    cl.pad2 = cr.pad2 = 0;
     cl.alive = left_alive;
     cr.alive = right_alive;
     cl.done = cr.done = 0;
@@ -1589,8 +1770,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
     if (threadIdx.x == 0) {
       a.gp->unresolved = 0;
       __threadfence();
-      *a.host_flag = FLAG_VALID | ((unsigned long long)(a.gp->rescale & 1u) << 33) |
-                     ((unsigned long long)a.gp->w_wide << 32);
+      *a.host_flag = FLAG_VALID | ((unsigned long long)(a.gp->wide & 1u) << 34) |
+                     ((unsigned long long)(a.gp->rescale & 1u) << 33) | ((unsigned long long)a.gp->w_wide << 32);
       __threadfence_system();
     }
     return;

@@ -40,13 +40,14 @@ typedef struct coupe_b200_stats {
 	uint32_t refine_sweeps;  /* sparse refinement passes */
 	uint32_t kernel_launches;/* CUDA kernels launched by the call */
 	uint32_t collectives;    /* NCCL calls issued by the call */
-	int32_t  weight_shift;   /* fixed-point shift used for f64 weights */
+	int32_t  weight_shift;   /* f64 weights: one accumulator unit is 2^-weight_shift (wide form: at the root node) */
 	uint32_t host_syncs;     /* stream synchronisations inside the call */
 	uint32_t flag_waits;     /* passes whose result the host polled for (mapped host memory) */
 	uint32_t peer_exchange;  /* 1: histograms went through the peer-memory exchange, 0: NCCL / single GPU */
 	uint32_t carry_free;     /* 1: integer weights small enough for 32-bit block-private sums (no carry chain in the sweeps) */
-	uint32_t reserved;
-	uint32_t weight_rescales; /* f64 weights: 1 when the sampled max |w| missed the exponent and the root pass was redone */
+	uint32_t weight_wide;    /* f64 weights: 0 narrow form (i32 multiples of one unit), 1 wide form (i64, one unit per tree node) */
+	uint32_t weight_rescales; /* f64 weights: root passes redone because the sampled weight statistics chose another form or scale
+	                             than all the weights do, or because the wide form wanted a finer root unit (0..2) */
 	double   matrix[9];      /* RIB: the obb_to_aabb matrix applied (row-major DxD) */
 	double   dense_sweep_ms; /* option "time_sweeps": summed device time of the dense sweeps */
 	double   refine_sweep_ms;/* option "time_sweeps": summed device time of the refinement sweeps */

@@ -62,6 +62,7 @@ def lib():
         _lib.oracle_inertia_matrix.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib.oracle_inertia_vector.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         _lib.oracle_householder.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oracle_last_wide.restype = C.c_int
         _lib.oracle_fix_shift.restype = C.c_int
         _lib.oracle_fix_shift.argtypes = [C.c_size_t, C.c_double]
         _lib.oracle_imbalance.restype = C.c_double
@@ -95,7 +96,8 @@ class Trace:
     n_items: np.ndarray
     n_left: np.ndarray
     iters: np.ndarray
-    shift: int = 0
+    shift: int = 0   # mode >= 1, f64 weights: fixed-point shift (of the root node in the wide form)
+    wide: int = 0    # ... 1 when the wide (per-node, 64-bit) form was used
 
 
 def _wtype_of(weights) -> int:
@@ -142,12 +144,15 @@ def _run(fn, points, weights, iter_count, tolerance, mode, want_trace, extra=())
         raise RuntimeError(f"oracle returned coupe_err {err}")
     if tr is not None:
         tr.shift = shift.value
+        tr.wide = lib().oracle_last_wide()
     return part, tr
 
 
 def rcb(points, weights, iter_count, tolerance=0.05, mode=0, trace=False):
     """Oracle Rcb.  points (n, D) f64; weights: int32/int64/float64 array of n,
-    or a 0-d array for a constant.  mode 0 native sums, 1 fixed-point f64 sums."""
+    or a 0-d array for a constant.  mode 0: the reference's native sums; 1: the GPU
+    path's exact fixed-point accumulation of f64 weights (narrow or wide form, chosen from the
+    weights); 2 / 3: that with the narrow / wide form forced."""
     part, tr = _run(lib().oracle_rcb, points, weights, iter_count, tolerance, mode, trace)
     return (part, tr) if trace else part
 

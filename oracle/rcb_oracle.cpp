@@ -27,10 +27,21 @@
 //   mode 0 "native":  sums in W exactly like the reference (i32/i64 wrapping,
 //                     f64 in chunked order: rayon's order is nondeterministic,
 //                     ours is fixed: 4096-element chunks combined left to right).
-//   mode 1 "fixed":   f64 weights are first quantised to i64 fixed point with
-//                     the documented shift (DESIGN.md "fixed-point weights");
-//                     this is the accumulation the GPU path uses, so part ids
-//                     can be compared bit-exactly.  Integer weights ignore it.
+//   mode 1 "gpu":     the accumulation the GPU path uses for f64 weights, so part
+//                     ids and the split tree can be compared bit-exactly (DESIGN.md
+//                     "f64 weights").  Exact integer sums of quantised weights, in
+//                     one of two forms chosen from the weights themselves:
+//                       narrow: i32 multiples of 2^-s, ONE global s, when that is
+//                               provably within 2^-30 relative of the real sums (no
+//                               negative weight, and every weight either exactly
+//                               representable or at least 2^(29-s));
+//                       wide:   i64 multiples of 2^-s_node with s_node chosen per
+//                               tree node from the node's own weight (the node sum
+//                               lands in [2^59, 2^61)): a partial sum of a node of
+//                               m points is within m * 2^-60 relative of the real
+//                               one whatever the dynamic range of the weights.
+//                     Integer weights ignore the mode.
+//   mode 2 / mode 3:  mode 1 with the narrow / wide form forced (experiments).
 // ---------------------------------------------------------------------------
 #include <algorithm>
 #include <cmath>
@@ -73,17 +84,36 @@ struct PolF64 {
   bool lt(T a, T b) const { return a < b; }
   double f64(T a) const { return a; }
 };
-// f64 weights quantised to i64 multiples of q = 2^-shift (GPU accumulation).
-struct PolFix {
+// f64 weights in the GPU path's fixed point (mode >= 1): i64 multiples of 2^(ec - shift).  Narrow
+// form: one shift for the whole tree (per_node false).  Wide form: the shift of the tree node being
+// split.  A child starts from its parent's shift and raises it until its own weight (handed down by the
+// parent, exact in the parent's units) lies in [2^59, 2^60); its points are then quantised afresh
+// from the caller's f64 weights.  With a negative weight somewhere every node keeps the root's shift.
+struct PolWide {
   using T = int64_t;
-  double q;
+  int shift;   // of the weights normalised by 2^-ec (largest |w| in [0.5, 1))
+  bool per_node;
+  int ec;
   T zero() const { return 0; }
   T add(T a, T b) const { return (T)((uint64_t)a + (uint64_t)b); }
   T sub(T a, T b) const { return (T)((uint64_t)a - (uint64_t)b); }
-  // the reference compares f64 values: `weight_left < sum - weight_left`
   bool lt(T a, T b) const { return f64(a) < f64(b); }
-  double f64(T a) const { return (double)a * q; }
+  double f64(T a) const { return std::ldexp((double)a, ec - shift); }
 };
+constexpr int kShiftMax = 1000;
+inline int bit_length(int64_t v) {  // v > 0
+  int l = 0;
+  while (v) {
+    ++l;
+    v >>= 1;
+  }
+  return l;
+}
+// round_to_nearest_even((w * 2^-ec) * 2^shift): two exact scalings (the first one rounds only
+// when it lands among the denormals, i.e. for weights 2^-1000 below the largest)
+inline int64_t quantise_wide(double w, int ec, int shift) {
+  return (int64_t)std::llrint(std::ldexp(std::ldexp(w, -ec), shift));
+}
 
 struct Trace {  // one entry per internal tree node, heap order (root = 0)
   uint8_t *visited;
@@ -101,6 +131,7 @@ struct Items {  // recursive_bisection.rs:105-109 (parts = index of the point)
   typename P::T *w;
   size_t *idx;
   size_t n;
+  double *wf = nullptr;  // wide f64 accumulation only: the caller's weights, reordered with the items
 };
 
 // reorder_split_scalar, recursive_bisection.rs:122-181.  `pivot` is the index
@@ -112,6 +143,7 @@ size_t reorder_split(Items<P> it, size_t pivot, int coord) {
     for (int d = 0; d < D; ++d) std::swap(it.x[d][a], it.x[d][b]);
     std::swap(it.w[a], it.w[b]);
     std::swap(it.idx[a], it.idx[b]);
+    if (it.wf) std::swap(it.wf[a], it.wf[b]);
   };
   swap_all(0, pivot);
   const float pv = it.x[coord][0];
@@ -235,9 +267,26 @@ struct Box {  // BoundingBox<D>, geometry.rs:21-24 (kept in f64 like the referen
   double lo[3], hi[3];
 };
 
+// Hook run when a node is about to be split: identity for every accumulation but the wide one.
+template <class P>
+P enter_node(const P &pol, Items<P> &, typename P::T &, int) {
+  return pol;
+}
+template <>
+PolWide enter_node<PolWide>(const PolWide &pol, Items<PolWide> &it, int64_t &sum, int depth) {
+  if (!pol.per_node || depth == 0 || sum <= 0) return pol;
+  const int d = std::max(0, std::min(60 - bit_length(sum), kShiftMax - pol.shift));
+  if (d == 0) return pol;
+  PolWide child = pol;
+  child.shift = pol.shift + d;
+  sum <<= d;
+  for (size_t i = 0; i < it.n; ++i) it.w[i] = quantise_wide(it.wf[i], child.ec, child.shift);
+  return child;
+}
+
 // rcb_recurse, recursive_bisection.rs:575-642.
 template <class P, int D>
-void rcb_recurse(const P &pol, Items<P> it, size_t iter_count, size_t iter_id, int coord,
+void rcb_recurse(const P &pol_parent, Items<P> it, size_t iter_count, size_t iter_id, int coord,
                  double tolerance, typename P::T sum, Box bb, uint64_t *partition, Trace *tr,
                  int depth) {
   if (it.n == 0) return;  // :586-588
@@ -245,6 +294,7 @@ void rcb_recurse(const P &pol, Items<P> it, size_t iter_count, size_t iter_id, i
     for (size_t i = 0; i < it.n; ++i) partition[it.idx[i]] = iter_id;
     return;
   }
+  const P pol = enter_node<P>(pol_parent, it, sum, depth);
   const float min = (float)bb.lo[coord];  // :604-605
   const float max = (float)bb.hi[coord];
   const bool parallel = it.n >= 8 * kGrain;
@@ -267,6 +317,7 @@ void rcb_recurse(const P &pol, Items<P> it, size_t iter_count, size_t iter_id, i
   for (int d = 0; d < D; ++d) right.x[d] = it.x[d] + s.n_left;
   right.w = it.w + s.n_left;
   right.idx = it.idx + s.n_left;
+  if (it.wf) right.wf = it.wf + s.n_left;
   const typename P::T wr = pol.sub(sum, s.weight_left);
   const int next = (coord + 1) % D;
   // rayon::join (:618-641) -> two tasks while the subtrees are large
@@ -283,7 +334,7 @@ void rcb_recurse(const P &pol, Items<P> it, size_t iter_count, size_t iter_id, i
 // rcb(), recursive_bisection.rs:644-705, after weights were collected into W.
 template <class P, int D>
 void rcb_run(const P &pol, size_t n, const double *pts, std::vector<typename P::T> &w,
-             size_t iter_count, double tolerance, uint64_t *partition, Trace *tr) {
+             size_t iter_count, double tolerance, uint64_t *partition, Trace *tr, double *wf = nullptr) {
   if (n == 0) return;  // BoundingBox::from_points -> None, :685-688
   std::vector<float> xs[3];
   for (int d = 0; d < D; ++d) {  // :674-679, f64 -> f32 narrowing (round to nearest even)
@@ -326,6 +377,7 @@ void rcb_run(const P &pol, size_t n, const double *pts, std::vector<typename P::
   it.w = w.data();
   it.idx = idx.data();
   it.n = n;
+  it.wf = wf;
 #pragma omp parallel
 #pragma omp single
   rcb_recurse<P, D>(pol, it, iter_count, 0, 0, tolerance, sum, bb, partition, tr, 0);
@@ -337,23 +389,73 @@ void rcb_run(const P &pol, size_t n, const double *pts, std::vector<typename P::
   for (long long i = 0; i < (long long)n; ++i) partition[i] -= off;
 }
 
-// Documented fixed-point shift shared (as a convention, not as code) with the
-// GPU path: weights become round_to_nearest_even(w * 2^shift).
-int fix_shift(size_t n, double maxabs) {
+// Fixed-point scales, shared (as a convention, not as code) with the GPU path.  Weights are
+// first normalised by 2^-ec, ec = exponent of the largest |w| (|w| < 2^ec, clamped so that
+// 2^-ec is a finite double), then become round_to_nearest_even(w' * 2^s): narrow form
+// s = min(31, 62 - nbits) for n <= 2^nbits points (i32 values, i64 sums); root of the wide
+// form s = 62 - nbits (n such values cannot overflow 2^62).
+int ceil_log2(size_t n) {
+  int nbits = 0;
+  while (nbits < 63 && ((size_t)1 << nbits) < n) ++nbits;
+  return nbits;
+}
+int weight_exponent(double maxabs) {
   if (!(maxabs > 0.0) || !std::isfinite(maxabs)) return 0;
   int e;
   std::frexp(maxabs, &e);  // maxabs = f * 2^e, f in [0.5, 1)  =>  maxabs < 2^e
-  int nbits = 0;
-  while (nbits < 63 && ((size_t)1 << nbits) < n) ++nbits;
-  int s = std::min(31 - e, 62 - e - nbits);
-  return std::max(-1000, std::min(1000, s));
+  return std::max(-1021, e);
 }
+int narrow_shift(size_t n) { return std::min(31, 62 - ceil_log2(n)); }
+int wide_shift(size_t n) { return 62 - ceil_log2(n); }
+// the narrow form's shift with respect to the weights as supplied (what the GPU reports)
+int fix_shift(size_t n, double maxabs) {
+  if (!(maxabs > 0.0) || !std::isfinite(maxabs)) return 0;
+  return narrow_shift(n) - weight_exponent(maxabs);
+}
+// Exponent of the lowest set bit of a non-zero finite double: w is a multiple of 2^this.
+int lsb_exponent(double w) {
+  uint64_t b;
+  std::memcpy(&b, &w, 8);
+  const int ex = (int)((b >> 52) & 0x7ff);
+  uint64_t mant = b & ((1ull << 52) - 1);
+  int E = -1074;
+  if (ex) {
+    mant |= 1ull << 52;
+    E = ex - 1075;
+  }
+  return E + __builtin_ctzll(mant);
+}
+
+// Which form the GPU path gives per-point f64 weights (DESIGN.md "f64 weights"): narrow when
+// no weight is negative and every sum is provably within 2^-30 relative: all weights multiples
+// of 2^-s (exact), or none (but zeros) below 2^(29-s) (each rounding error is at most
+// 2^-(s+1), i.e. 2^-30 of the smallest weight).
+bool narrow_form_ok(size_t n, const double *w, int s /* with respect to the weights as supplied */) {
+  bool neg = false, any = false;
+  int lsb = 1 << 20;
+  double wmin = std::numeric_limits<double>::infinity();
+  for (size_t i = 0; i < n; ++i) {
+    if (w[i] < 0.0) neg = true;
+    const double a = std::fabs(w[i]);
+    if (a > 0.0 && std::isfinite(a)) {
+      any = true;
+      lsb = std::min(lsb, lsb_exponent(a));
+      wmin = std::min(wmin, a);
+    }
+  }
+  if (neg) return false;
+  if (!any) return true;
+  return lsb + s >= 0 || wmin >= std::ldexp(1.0, 29 - s);
+}
+
+int g_last_wide = 0;  // form the last mode >= 1 call used for f64 weights (oracle_last_wide)
 
 template <int D>
 int rcb_dispatch(uint64_t *partition, size_t n, const double *pts, int wtype, const void *w,
                  int w_is_const, size_t iter_count, double tolerance, int mode, Trace *tr,
                  int *shift_out) {
   if (shift_out) *shift_out = 0;
+  g_last_wide = 0;
   if (wtype == 0) {
     std::vector<int32_t> wv(n);
     const int32_t *src = (const int32_t *)w;
@@ -372,17 +474,42 @@ int rcb_dispatch(uint64_t *partition, size_t n, const double *pts, int wtype, co
   } else if (wtype == 2) {
     const double *src = (const double *)w;
     double maxabs = 0.0;
-    for (size_t i = 0; i < (w_is_const ? (n ? 1 : 0) : n); ++i)
+    bool neg = false;
+    for (size_t i = 0; i < (w_is_const ? (n ? 1 : 0) : n); ++i) {
       maxabs = std::max(maxabs, std::fabs(src[i]));
-    const int s = fix_shift(n, maxabs);
-    if (shift_out) *shift_out = s;
-    std::vector<int64_t> wv(n);
-    for (size_t i = 0; i < n; ++i) {  // round to nearest even, saturating to the i32 range
-      const int64_t v = (int64_t)std::llrint(std::ldexp(w_is_const ? src[0] : src[i], s));
-      wv[i] = std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, v));
+      neg = neg || src[i] < 0.0;
     }
-    rcb_run<PolFix, D>(PolFix{std::ldexp(1.0, -s)}, n, pts, wv, iter_count, tolerance, partition,
-                       tr);
+    const int ec = weight_exponent(maxabs), s = narrow_shift(n);
+    // a constant weight is one factor common to every sum: the narrow form loses nothing
+    const bool wide = w_is_const ? false : mode == 3 || (mode == 1 && !narrow_form_ok(n, src, s - ec));
+    g_last_wide = wide;
+    std::vector<int64_t> wv(n);
+    if (!wide) {
+      if (shift_out) *shift_out = s - ec;
+      for (size_t i = 0; i < n; ++i) {  // round to nearest even, saturating to the i32 range
+        const int64_t v = quantise_wide(w_is_const ? src[0] : src[i], ec, s);
+        wv[i] = std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, v));
+      }
+      rcb_run<PolWide, D>(PolWide{s, false, ec}, n, pts, wv, iter_count, tolerance, partition, tr);
+    } else {
+      // root: the coarse shift that cannot overflow; when that leaves the total below
+      // 2^(nbits+31) units (worst-case rounding n/2 units: above 2^-31 relative) and the weights
+      // are non-negative, the root is quantised again with its total in [2^59, 2^61)
+      int sw = wide_shift(n);
+      int64_t total = 0;
+      for (size_t i = 0; i < n; ++i) total += (wv[i] = quantise_wide(src[i], ec, sw));
+      if (!neg && total > 0 && bit_length(total) < ceil_log2(n) + 31) {
+        const int d = std::max(0, std::min(60 - bit_length(total), kShiftMax - sw));
+        if (d > 0) {
+          sw += d;
+          for (size_t i = 0; i < n; ++i) wv[i] = quantise_wide(src[i], ec, sw);
+        }
+      }
+      if (shift_out) *shift_out = sw - ec;
+      std::vector<double> wf(src, src + n);
+      rcb_run<PolWide, D>(PolWide{sw, !neg, ec}, n, pts, wv, iter_count, tolerance, partition, tr,
+                          wf.data());
+    }
   } else {
     return 4;  // COUPE_ERR_BAD_TYPE
   }
@@ -659,6 +786,7 @@ void oracle_householder(int dim, const double *v, double *h) {
   else householder<3>(v, h);
 }
 int oracle_fix_shift(size_t n, double maxabs) { return fix_shift(n, maxabs); }
+int oracle_last_wide(void) { return g_last_wide; }
 
 // imbalance(), coupe/src/imbalance.rs:42-78 (f64 loads).
 double oracle_imbalance(size_t num_parts, size_t n, const uint64_t *partition, int wtype,

@@ -52,6 +52,8 @@ def gen_weights(rng, n, kind):
         return rng.integers(1, 50, n).astype(np.float64)
     if kind == "f64":
         return rng.uniform(0.5, 1.5, n)
+    if kind == "f64wide":  # dynamic range far beyond one 31-bit scale: the wide form
+        return rng.lognormal(0.0, 5.0, n)
     if kind == "const_i32":
         return np.array(1, dtype=np.int32)
     if kind == "const_f64":
@@ -201,55 +203,102 @@ def test_rcb_f64_weights(cb, oracle, n, dim, pk, iters, tol):
     rng = np.random.default_rng(n + dim + iters)
     pts = gen_points(rng, n, dim, pk)
     w = gen_weights(rng, n, "f64")
-    got = run_device(cb, pts, w, iters, tol)
-    t = cb.default_context(0).trace(iters)
-    # (1) bit-exact against the oracle run with the same fixed-point accumulation
+    ctx = cb.Context(0)
+    got = run_device(cb, pts, w, iters, tol, ctx=ctx)
+    st = check_f64(cb, oracle, ctx, pts, w, iters, tol, got)
+    assert st["weight_wide"] == 0  # U[0.5, 1.5): provably within 2^-30 in the narrow form
+    ctx.close()
+
+
+def check_f64(cb, oracle, ctx, pts, w, iters, tol, got, negative=False):
+    """f64 weights: (1) bit-exact ids and split tree against the oracle run with the GPU path's accumulation
+    (mode 1: narrow or wide fixed point chosen from the weights); (2) against the reference's native f64
+    sums (mode 0): same ids and split positions; (3) left weights within 1e-9 of correctly rounded sums."""
+    from exact_tree import exact_tree
+    from test_oracle_f64_forms import tolerance_scale
+
+    t = ctx.trace(iters)
+    st = ctx.stats()
     want_fix, tr_fix = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
-    assert cb.default_context(0).stats()["weight_shift"] == tr_fix.shift
-    assert np.array_equal(got, want_fix)
+    assert st["weight_wide"] == tr_fix.wide
+    assert st["weight_shift"] == tr_fix.shift
+    assert np.array_equal(got, want_fix), f"{int((got != want_fix).sum())} ids differ from the oracle (mode 1)"
     assert np.array_equal(t["visited"], tr_fix.visited)
     vf = tr_fix.visited.astype(bool)
     assert np.array_equal(t["split_pos"][vf], tr_fix.split_pos[vf])
-    assert np.array_equal(t["weight_left"][vf], tr_fix.weight_left[vf])
     assert np.array_equal(t["iters"][vf], tr_fix.iters[vf])
-    # (2) against the oracle's native f64 sums: split positions identical here,
-    # left weights within 1e-9 relative (the north-star tolerance)
+    assert np.array_equal(t["weight_left"][vf], tr_fix.weight_left[vf])
+    assert np.array_equal(t["sum"][vf], tr_fix.sum[vf])
     want_nat, tr_nat = oracle.rcb(pts, w, iters, tol, mode=0, trace=True)
-    v = tr_nat.visited.astype(bool)
-    np.testing.assert_allclose(t["split_pos"][v], tr_nat.split_pos[v], rtol=1e-9, atol=0)
-    np.testing.assert_allclose(t["weight_left"][v], tr_nat.weight_left[v], rtol=1e-9, atol=0)
-    assert np.array_equal(got, want_nat)
+    assert np.array_equal(t["visited"], tr_nat.visited)
+    assert np.array_equal(t["split_pos"][vf], tr_nat.split_pos[vf])
+    assert np.array_equal(got, want_nat), f"{int((got != want_nat).sum())} ids differ from the oracle (mode 0)"
+    wl, total, ids = exact_tree(pts, w, t["visited"], t["split_pos"], iters)
+    assert np.array_equal(ids, got)
+    assert np.all(np.abs(t["weight_left"][vf] - wl[vf]) <= 1e-9 * tolerance_scale(total, tr_nat, w, negative)[vf])
     nparts = 1 << iters
     assert oracle.imbalance(nparts, got, w) == pytest.approx(oracle.imbalance(nparts, want_nat, w), rel=1e-9)
+    return st
 
 
-def test_f64_weight_scale_from_sample_is_verified(cb, oracle):
-    """max |w| is read from a sample of the weights (one run of 1024 points in 64); the root sweep checks
-    the exponent against the true maximum and the root pass is redone when an outlier was missed."""
+WIDE_NAMES = ["outlier1e+06", "outlier1e+12", "lognormal6", "spike", "two_scales", "linear", "tiny", "zeros",
+              "dyadic_wide_range", "negative"]
+
+
+@pytest.mark.parametrize("name", WIDE_NAMES)
+def test_rcb_f64_wide_range_weights(cb, oracle, name):
+    """Weights whose dynamic range one 31-bit scale cannot hold (round 1 turned the light ones into zeros):
+    the wide form, a 64-bit fixed point with one unit per tree node."""
+    from test_oracle_f64_forms import weight_cases
+
+    rng = np.random.default_rng(7)
+    n, iters, tol = 300_000, 8, 0.02
+    pts = rng.random((n, 3))
+    w, want_wide = weight_cases(rng, n, pts)[name]
+    ctx = cb.Context(0)
+    got = run_device(cb, pts, w, iters, tol, ctx=ctx)
+    st = check_f64(cb, oracle, ctx, pts, w, iters, tol, got, negative=name == "negative")
+    if want_wide is not None:
+        assert st["weight_wide"] == want_wide
+    ctx.close()
+
+
+def test_f64_weight_form_from_sample_is_verified(cb, oracle):
+    """Form and scale of the fixed point come from statistics of a sample of the weights (one run of 1024
+    points in 64); the root sweep computes them over all weights and the root pass is redone when they ask
+    for something else (an outlier, a tiny or a negative weight outside the sample)."""
     rng = np.random.default_rng(31)
     n = 300_000
     pts = rng.normal(size=(n, 3))
     w = rng.uniform(0.5, 1.5, n)
     ctx = cb.Context(0)
-    want = oracle.rcb(pts, w, 7, 0.02, mode=1)
-    assert np.array_equal(run_device(cb, pts, w, 7, 0.02, ctx=ctx), want)
-    assert ctx.stats()["weight_rescales"] == 0
-    for at, val in ((5000, 1000.0), (70_000, 3.0), (123_457, 1e12)):  # not in a sampled run: 0..1023, 65536..66559, ...
+    got = run_device(cb, pts, w, 7, 0.02, ctx=ctx)
+    st = check_f64(cb, oracle, ctx, pts, w, 7, 0.02, got)
+    assert st["weight_wide"] == 0 and st["weight_rescales"] == 0
+    # an exponent missed by the sample, still narrow (range below 4): 0..1023, 65536..66559, ... are sampled
+    w1 = rng.uniform(0.5, 1.0, n)
+    w1[5000] = 1.9
+    got = run_device(cb, pts, w1, 7, 0.02, ctx=ctx)
+    st = check_f64(cb, oracle, ctx, pts, w1, 7, 0.02, got)
+    assert st["weight_wide"] == 0 and st["weight_rescales"] == 1
+    assert st["weight_shift"] == oracle.fix_shift(n, 1.9)
+    for at, val in ((5000, 1000.0), (70_000, 1e-7), (123_457, 1e12), (200_001, -0.25)):  # outside every sampled run
         w2 = w.copy()
         w2[at] = val
-        want = oracle.rcb(pts, w2, 7, 0.02, mode=1)
-        assert np.array_equal(run_device(cb, pts, w2, 7, 0.02, ctx=ctx), want)
-        assert ctx.stats()["weight_rescales"] == 1
-        assert ctx.stats()["weight_shift"] == oracle.fix_shift(n, w2.max())
+        got = run_device(cb, pts, w2, 7, 0.02, ctx=ctx)
+        st = check_f64(cb, oracle, ctx, pts, w2, 7, 0.02, got, negative=val < 0)
+        assert st["weight_wide"] == 1 and st["weight_rescales"] >= 1
     w3 = w.copy()
-    w3[100] = 64.0  # inside the first sampled run: the sample already has the right exponent
-    assert np.array_equal(run_device(cb, pts, w3, 7, 0.02, ctx=ctx), oracle.rcb(pts, w3, 7, 0.02, mode=1))
-    assert ctx.stats()["weight_rescales"] == 0
+    w3[100] = 4096.0  # inside the first sampled run: the sample already asks for the wide form
+    got = run_device(cb, pts, w3, 7, 0.02, ctx=ctx)
+    st = check_f64(cb, oracle, ctx, pts, w3, 7, 0.02, got)
+    assert st["weight_wide"] == 1 and st["weight_rescales"] <= 1  # at most the finer root unit
     ctx.set_option("sample_weights", 0)
     w2 = w.copy()
     w2[5000] = 1000.0
-    assert np.array_equal(run_device(cb, pts, w2, 7, 0.02, ctx=ctx), oracle.rcb(pts, w2, 7, 0.02, mode=1))
-    assert ctx.stats()["weight_rescales"] == 0
+    got = run_device(cb, pts, w2, 7, 0.02, ctx=ctx)
+    st = check_f64(cb, oracle, ctx, pts, w2, 7, 0.02, got)
+    assert st["weight_wide"] == 1 and st["weight_rescales"] <= 1
     ctx.close()
 
 
@@ -342,7 +391,7 @@ def test_pass_schedules_do_not_change_results(cb, oracle, opts):
         ctx.set_option(k, v)
     rng = np.random.default_rng(77)
     for pk, wk, dim, iters, tol in [("cluster", "i64", 3, 9, 0.0), ("grid", "i32", 2, 8, 0.001),
-                                    ("negative", "f64", 3, 7, 0.05)]:
+                                    ("negative", "f64", 3, 7, 0.05), ("cluster", "f64wide", 3, 8, 0.01)]:
         pts = gen_points(rng, 60_001, dim, pk)
         w = gen_weights(rng, 60_001, wk)
         want, tr = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
@@ -364,7 +413,7 @@ def test_refinement_with_dense_matches(cb, oracle):
     pts = rng.random((n, 3))
     tight = rng.random(n) < 0.9
     pts[tight] = 0.37 + rng.normal(size=(int(tight.sum()), 3)) * 1e-5
-    for wk, tol in (("i64", 0.0), ("f64", 0.01)):
+    for wk, tol in (("i64", 0.0), ("f64", 0.01), ("f64wide", 0.01)):
         w = gen_weights(rng, n, wk)
         for opts in ({}, {"kmax_a": 3, "kmax_refine": 4}):
             ctx = cb.Context(0)
@@ -411,6 +460,8 @@ def test_rib_against_oracle(cb, oracle, dim):
     (4_000_003, 3, "cluster", "f64", 10, 0.05),   # full 148-block grid, refinement sweeps, f64 fixed point
     (3_000_001, 2, "uniform", "i64", 12, 0.05),   # config C2 in miniature: 4096 parts, bit-exact integer weights
     (2_500_000, 3, "grid", "f64int", 10, 0.001),  # config C3's shape: heavy coordinate duplication, tight tolerance
+    (4_000_003, 3, "cluster", "f64wide", 10, 0.02),  # wide form on the full grid: f64 weights re-read and re-quantised per level
+    (2_000_001, 2, "gauss", "f64wide", 13, 0.05),    # ... with levels beyond the shared-memory histograms (L2 atomics)
 ])
 def test_full_grid_sizes_against_oracle(cb, oracle, n, dim, pk, wk, iters, tol):
     rng = np.random.default_rng(n % 1000)

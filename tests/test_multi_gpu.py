@@ -1,5 +1,5 @@
-"""Two GPUs, one process each: sharded RCB / RIB give exactly the ids of the
-single-GPU run on the concatenated input (and of the oracle)."""
+"""2, 4 and 8 GPUs (as many as the box has), one process each: sharded RCB / RIB give exactly the
+ids of the single-GPU run on the concatenated input (and of the oracle)."""
 import os
 import socket
 
@@ -75,6 +75,11 @@ def two_gpus():
         pytest.skip("needs two CUDA devices")
 
 
+def _world_or_skip(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} CUDA devices")
+
+
 @pytest.mark.parametrize("peer", [True, False], ids=["peer-exchange", "nccl"])
 @pytest.mark.parametrize("wkind,dim,iters,tol,empty_last", [
     ("i64", 3, 10, 0.05, False),
@@ -84,8 +89,29 @@ def two_gpus():
     ("f64outlier", 3, 8, 0.05, False),  # one huge weight on the second rank, outside every sampled run
     ("i64", 2, 6, 0.05, True),          # array weights and an empty last shard: same collective steps on every rank
     ("f64", 3, 6, 0.05, True),
+    ("f64lognormal", 3, 8, 0.02, False),  # wide form: per-node units, f64 weights re-read at every level
+    ("f64negative", 2, 7, 0.05, True),    # ... with one global unit, found by the rank that holds the negative weight
 ])
 def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, empty_last, peer):
+    check_sharded(oracle, wkind, dim, iters, tol, empty_last, peer, 2)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+@pytest.mark.parametrize("wkind,dim,iters,tol,empty_last,peer", [
+    ("i64", 3, 10, 0.05, False, True),
+    ("f64", 3, 10, 0.05, False, True),
+    ("f64", 3, 9, 0.05, True, False),
+    ("f64lognormal", 3, 9, 0.02, False, True),
+    ("f64outlier", 2, 8, 0.05, True, True),
+    ("const", 3, 8, 0.0, False, True),
+])
+def test_sharded_rcb_matches_oracle_4_and_8_gpus(oracle, world, wkind, dim, iters, tol, empty_last, peer):
+    """The exchange layout (XCHG_DEPTH slots x world sources) and the flag protocol at world sizes above 2."""
+    _world_or_skip(world)
+    check_sharded(oracle, wkind, dim, iters, tol, empty_last, peer, world)
+
+
+def check_sharded(oracle, wkind, dim, iters, tol, empty_last, peer, world):
     rng = np.random.default_rng(11)
     n = 300_007
     k = rng.integers(0, 5, n)
@@ -94,9 +120,13 @@ def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, em
          "i64big": rng.integers(1, 2**40, n).astype(np.int64),
          "f64": rng.uniform(0.5, 1.5, n),
          "f64outlier": np.where(np.arange(n) == n - 77_777, 1e9, rng.uniform(0.5, 1.5, n)),
+         "f64lognormal": rng.lognormal(0.0, 5.0, n),
+         "f64negative": np.where(np.arange(n) == n - 99_999, -0.125, rng.uniform(0.5, 1.5, n)),
          "const": np.array(3, dtype=np.int32)}[wkind]
-    got = run_sharded((pts, w, iters, tol, False, empty_last, peer))
+    got = run_sharded((pts, w, iters, tol, False, empty_last, peer), world)
     assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=1))
+    if wkind.startswith("f64"):  # and the reference's native f64 sums
+        assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=0))
 
 
 def test_sharded_rib_matches_single_gpu(two_gpus):

@@ -17,7 +17,7 @@ def main():
     ap.add_argument("--dim", type=int, default=3)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--tol", type=float, default=0.05)
-    ap.add_argument("--w", default="f64", choices=["f64", "i64", "i32", "const"])
+    ap.add_argument("--w", default="f64", choices=["f64", "f64wide", "i64", "i32", "const"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "gauss", "grid"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--opt", action="append", default=[])
@@ -52,6 +52,8 @@ def main():
         w = (pts[:, 0] - 0.5) * (100.0 / 399.0)
     elif a.w == "f64":
         w = torch.rand(a.n, dtype=torch.float64, device=dev, generator=g) + 0.5
+    elif a.w == "f64wide":  # log-normal, sigma 4: the wide fixed-point form
+        w = torch.exp(torch.randn(a.n, dtype=torch.float64, device=dev, generator=g) * 4.0)
     elif a.w == "i64":
         w = torch.randint(1, 100, (a.n,), dtype=torch.int64, device=dev, generator=g)
     elif a.w == "i32":
@@ -75,7 +77,7 @@ def main():
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     st = ctx.stats()
-    wbytes = {"f64": 8, "i64": 8, "i32": 4, "const": 0}[a.w]
+    wbytes = {"f64": 8, "f64wide": 8, "i64": 8, "i32": 4, "const": 0}[a.w]
     algo_bytes = a.n * (a.iters * (16 + wbytes) + 8 * a.dim + wbytes + 12)
     if not ts:
         return
