@@ -23,7 +23,7 @@ COUPE_B200_H_SYMBOLS = ["coupe_b200_ctx_create", "coupe_b200_ctx_destroy", "coup
                         "coupe_b200_nccl_unique_id",
                         "coupe_b200_ctx_init_comm", "coupe_b200_rcb_device", "coupe_b200_rib_device",
                         "coupe_b200_rcb_host", "coupe_b200_rib_host", "coupe_b200_host_release",
-                        "coupe_b200_last_stats", "coupe_b200_last_trace", "coupe_b200_reserve",
+                        "coupe_b200_last_stats", "coupe_b200_last_sweep_times", "coupe_b200_last_trace", "coupe_b200_reserve",
                         "coupe_b200_set_option", "coupe_b200_version"]
 # include/coupe_b200_tools.h
 COUPE_B200_TOOLS_H_SYMBOLS = ["coupe_b200_barycentres_device", "coupe_b200_weight_linear_device",
@@ -106,6 +106,8 @@ def lib():
     L.coupe_b200_host_release.argtypes = [C.c_void_p]
     L.coupe_b200_last_stats.restype = C.c_int
     L.coupe_b200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.coupe_b200_last_sweep_times.restype = C.c_uint32
+    L.coupe_b200_last_sweep_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     L.coupe_b200_last_trace.restype = C.c_int
     L.coupe_b200_last_trace.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.coupe_b200_reserve.restype = C.c_int

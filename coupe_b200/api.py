@@ -88,6 +88,13 @@ class Context:
         _lib.lib().coupe_b200_last_stats(self._h, C.byref(s))
         return s.as_dict()
 
+    def sweep_times(self):
+        """Option time_sweeps: [(ms, level, kind)] of every timed sweep of the last call (kind 0 dense, 1 refinement)."""
+        cap = 256
+        ms, lv, kd = np.zeros(cap), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        m = _lib.lib().coupe_b200_last_sweep_times(self._h, ms.ctypes.data, lv.ctypes.data, kd.ctypes.data, cap)
+        return [(float(ms[i]), int(lv[i]), int(kd[i])) for i in range(min(m, cap))]
+
     def trace(self, iter_count: int):
         """Split tree of the last call in heap order (see coupe_b200_last_trace)."""
         m = max((1 << iter_count) - 1, 0)

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <string>
 #include <vector>
 
@@ -21,7 +22,9 @@ namespace {
 
 using namespace cb;
 
-constexpr int MAX_LEVELS = 20;
+// Node tables are dense arrays of 2^level entries replicated on every GPU: 2^24 parts is where they reach a few GB.
+// Beyond that the call returns COUPE_ERR_ALLOC (documented in coupe.h); the reference itself recurses to any depth.
+constexpr int MAX_LEVELS = 24;
 constexpr uint64_t FLAG_SLOTS = 256;  // passes in flight are at most a handful  // 2^20 parts; node tables are replicated on every GPU
 
 struct CudaFail {
@@ -233,6 +236,8 @@ struct coupe_b200_ctx {
   int sample_w_opt = 1;  // f64 weights: max |w| from a sample, verified by the root sweep
   std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
   std::vector<int> event_kind;      // 0 dense, 1 refine
+  std::vector<int> event_level;     // tree level of the sweep
+  std::vector<double> sweep_ms;     // time_sweeps: device time of every timed sweep of the last call
   // last call
   coupe_b200_stats stats{};
   uint32_t trace_levels = 0;
@@ -352,6 +357,20 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
   return p;
 }
 
+// NVTX ranges around the whole call and around every pass as it is enqueued: the counterpart of
+// the reference's tracing spans (recursive_bisection.rs:467-468 "rcb_split", :590-595 "rcb_recurse").
+// The kernels of a pass run asynchronously; a timeline tool projects the range onto the stream.
+struct NvtxRange {
+  template <class... A>
+  explicit NvtxRange(const char *fmt, A... a) {
+    char buf[96];
+    snprintf(buf, sizeof buf, fmt, a...);
+    nvtxRangePushA(buf);
+  }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+};
+
 struct Run {
   coupe_b200_ctx *c;
   cudaStream_t st;
@@ -374,10 +393,11 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   if (dim != 2 && dim != 3) return COUPE_ERR_BAD_DIMENSION;
   if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
   if (n > 0 && !w_dev && !wconst_host) return COUPE_ERR_CRASH;
-  if (iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_CRASH;
-  if (n >= ((uintptr_t)1 << 32) * 4) return COUPE_ERR_CRASH;
+  if (iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_ALLOC;  // tables of 2^iter_count nodes (see MAX_LEVELS)
+  if (n >= ((uintptr_t)1 << 32) * 4) return COUPE_ERR_ALLOC;       // more points than one GPU's HBM holds
   CU(cudaSetDevice(c->device));
   prepare_funcs(c);
+  NvtxRange call_range("coupe_b200 %s: %zu points, %d levels", rib ? "rib" : "rcb", (size_t)n, (int)iter_count);
   const int D = (int)dim, L = (int)iter_count;
   c->stats = coupe_b200_stats{};
   coupe_b200_stats &S = c->stats;
@@ -562,9 +582,12 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   }
 
   size_t ev_used = 0;
+  int last_first_pass_event = -1;  // index (event_kind) of the dense sweep enqueued last, when it is being timed
   c->event_kind.clear();
+  c->event_level.clear();
+  c->sweep_ms.clear();
   bool timing_open = false;
-  auto time_begin = [&](int kind) {  // option time_sweeps: 1 = dense sweeps, 2 = refinement sweeps too (and print)
+  auto time_begin = [&](int kind, int level) {  // option time_sweeps: 1 = dense sweeps, 2 = refinement sweeps too, 3 = and print
     timing_open = c->time_sweeps > kind;
     if (!timing_open) return;
     while (c->events.size() < ev_used + 2) {
@@ -573,6 +596,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       c->events.push_back(e);
     }
     c->event_kind.push_back(kind);
+    c->event_level.push_back(level);
     CU(cudaEventRecord(c->events[ev_used], st));
   };
   auto time_end = [&]() {
@@ -626,6 +650,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   const uint32_t *guard_ptr = &gp->unresolved;
   uint32_t w_wide = 0, rescale = 0, f64_wide = 0;
   uint64_t seq = c->flag_seq;
+  // whatever way the call ends (error returns and exceptions included) the next call must not reuse the
+  // sequence numbers of passes already enqueued: host flags and exchange slots still carry them
+  struct SeqGuard {
+    uint64_t &dst;
+    const uint64_t &src;
+    ~SeqGuard() { dst = src; }
+  } seq_guard{c->flag_seq, seq};
   auto flag_slot = [&](uint64_t s) { return s % FLAG_SLOTS; };
   auto wait_flag = [&](uint64_t s) -> uint32_t {
     volatile unsigned long long *f = c->h_flags + flag_slot(s);
@@ -667,6 +698,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   };
   // the dense first pass of `level`; kprev = bins of the level before
   auto enqueue_first_pass = [&](int level, int kprev, const uint32_t *guard) {
+    NvtxRange range("rcb level %d: dense pass%s", level, guard ? " (optimistic)" : "");
     const int axis = level % D, prev_axis = (level + D - 1) % D;
     const FirstPlan plan = plan_first(c, level);
     const int k = plan.k;
@@ -699,7 +731,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       launch_pdl(fill_hist_kernel, (nb + 255) / 256, 256, 0, st, hist_w, hist_min, nb, guard);
       R.launched();
     }
-    time_begin(0);
+    time_begin(0, level);
+    last_first_pass_event = timing_open ? (int)c->event_kind.size() - 1 : -1;
     launch_sweep_any(win, level == 0, plan.smem, plan.table_in_smem, idx16, sweep_grid, plan.bytes, st, sa);
     time_end();
     R.launched();
@@ -714,6 +747,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     return enqueue_walk(level, k, k, 1, 0, guard);
   };
   auto enqueue_refine_round = [&](int level, int k0, uint32_t unresolved) {
+    NvtxRange range("rcb level %d: refinement pass, %u undecided nodes", level, unresolved);
     // ranked histograms of as many undecided nodes as shared memory holds, 2^kr bins each
     const int axis = level % D;
     bool rts;
@@ -725,7 +759,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const size_t rbytes = (size_t)REFINE_QBYTES + (size_t)nslots * 12 + (rts ? rt_bytes : 0);
     RefineArgs ra{n, x[axis], ids, wp, node_rt, rtable, rfast, c->part_w.as<long long>(),
                   c->part_min.as<uint32_t>(), nslots, limit, level, kr, k0, rts, 1u, gp, nsh_cur};
-    time_begin(1);
+    time_begin(1, level);
     switch (win) {
       case WIN_I32: launch_refine<WIN_I32>(idx16, rts, sweep_grid, rbytes, st, ra); break;
       case WIN_I64: launch_refine<WIN_I64>(idx16, rts, sweep_grid, rbytes, st, ra); break;
@@ -815,7 +849,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     }
     if (unresolved > 0) {
       // the optimistic pass (if any) returned at once on the device; refine this level, then redo it
-      if (speculated && level + 1 < L) S.dense_sweeps -= 1;
+      if (speculated && level + 1 < L) {
+        S.dense_sweeps -= 1;
+        if (last_first_pass_event >= 0) c->event_kind[last_first_pass_event] = 2;  // returned at once: not a sweep
+      }
       advance_level();  // back to this level's tables
       int guard = 0;
       while (unresolved > 0) {
@@ -831,7 +868,6 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     }
     pending = next_pending;
   }
-  c->flag_seq = seq;
   CU(cudaMemcpyAsync(c->h_pinned + 2, &gp->refine_points, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned + 6, &gp->ec, 4, cudaMemcpyDeviceToHost, st));
@@ -855,8 +891,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   for (size_t e = 0; e + 1 < ev_used; e += 2) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->events[e], c->events[e + 1]));
-    (c->event_kind[e / 2] ? S.refine_sweep_ms : S.dense_sweep_ms) += ms;
-    if (c->time_sweeps > 1) fprintf(stderr, "coupe_b200: %s sweep %zu: %.1f us\n", c->event_kind[e / 2] ? "refine" : "dense", e / 2, ms * 1e3);
+    const int kind = c->event_kind[e / 2];
+    if (kind == 0) S.dense_sweep_ms += ms;
+    if (kind == 1) S.refine_sweep_ms += ms;
+    c->sweep_ms.push_back(ms);
+    if (c->time_sweeps > 2)
+      fprintf(stderr, "coupe_b200: level %d %s sweep %zu: %.1f us\n", c->event_level[e / 2],
+              kind == 0 ? "dense" : kind == 1 ? "refine" : "(void optimistic)", e / 2, ms * 1e3);
   }
   CU(cudaGetLastError());
   return COUPE_ERR_OK;
@@ -1076,6 +1117,17 @@ int coupe_b200_last_stats(const coupe_b200_ctx *ctx, coupe_b200_stats *out) {
   return COUPE_ERR_OK;
 }
 
+uint32_t coupe_b200_last_sweep_times(const coupe_b200_ctx *c, double *ms, int32_t *level, int32_t *kind, uint32_t cap) {
+  if (!c) return 0;
+  const uint32_t m = (uint32_t)c->sweep_ms.size();
+  for (uint32_t i = 0; i < m && i < cap; ++i) {
+    if (ms) ms[i] = c->sweep_ms[i];
+    if (level) level[i] = c->event_level[i];
+    if (kind) kind[i] = c->event_kind[i];
+  }
+  return m;
+}
+
 int coupe_b200_last_trace(coupe_b200_ctx *c, uint8_t *visited, float *split_pos, double *weight_left,
                           double *sum, uint32_t *iters) {
   if (!c || !c->trace_on) return COUPE_ERR_CRASH;
@@ -1093,7 +1145,8 @@ int coupe_b200_last_trace(coupe_b200_ctx *c, uint8_t *visited, float *split_pos,
 }
 
 int coupe_b200_reserve(coupe_b200_ctx *c, uintptr_t n, uintptr_t dim, uintptr_t iter_count) {
-  if (!c || (dim != 2 && dim != 3) || iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_CRASH;
+  if (!c || (dim != 2 && dim != 3)) return COUPE_ERR_CRASH;
+  if (iter_count > (uintptr_t)MAX_LEVELS) return COUPE_ERR_ALLOC;
   std::lock_guard<std::mutex> lock(c->mu);
   try {
     CU(cudaSetDevice(c->device));

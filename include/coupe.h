@@ -72,6 +72,9 @@ coupe_data *coupe_data_fn(const void *context, uintptr_t len, enum coupe_type ty
  * `partition` (N uintptr_t, fully overwritten when N > 0, ids start at 0).
  * Errors: dimension not in {2,3} -> BAD_DIMENSION; length mismatch ->
  * LEN_MISMATCH; unknown weight tag -> BAD_TYPE; device trouble -> ALLOC/CRASH.
+ * Limit of this implementation (the reference recurses to any depth): the node
+ * tables hold 2^iter_count entries on every GPU, so iter_count > 24 (more
+ * than 2^24 parts) returns COUPE_ERR_ALLOC without touching `partition`.
  */
 enum coupe_err coupe_rcb(uintptr_t *partition, uintptr_t dimension,
 		const coupe_data *points, const coupe_data *weights,

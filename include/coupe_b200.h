@@ -107,6 +107,13 @@ void coupe_b200_host_release(coupe_b200_ctx *ctx);
 /* Counters of the last call. */
 int coupe_b200_last_stats(const coupe_b200_ctx *ctx, coupe_b200_stats *out);
 
+/* Option "time_sweeps": device time (CUDA events on the call's stream) of every timed sweep of the
+ * last call, in launch order: milliseconds, tree level, kind (0 dense sweep, 1 refinement sweep, 2 an
+ * optimistic dense sweep that found the previous level undecided and returned at once).
+ * Writes at most `cap` entries (arrays may be NULL) and returns how many sweeps were timed. */
+uint32_t coupe_b200_last_sweep_times(const coupe_b200_ctx *ctx, double *ms, int32_t *level, int32_t *kind,
+		uint32_t cap);
+
 /*
  * Split tree of the last call, heap order (root 0, children 2i+1 / 2i+2),
  * 2^iter_count - 1 entries each, copied to HOST arrays (any may be NULL):
@@ -127,9 +134,9 @@ int coupe_b200_reserve(coupe_b200_ctx *ctx, uintptr_t n, uintptr_t dim, uintptr_
  *   nb_smem_log2 (6..14, 14) histogram slots a block keeps in shared memory
  *   force_global (0)         accumulate with L2 atomics instead of shared-memory histograms
  *   trace (1)                keep the split tree for coupe_b200_last_trace
- *   time_sweeps (0)          1: CUDA events around the dense sweeps, 2: refinement sweeps too (printed)
+ *   time_sweeps (0)          1: CUDA events around the dense sweeps, 2: refinement sweeps too, 3: and print them
  *   peer_exchange (1)        multi-GPU: histograms over peer memory (0: NCCL all-reduces)
- *   sample_weights (1)       f64 weights: max |w| from a sample, verified by the root sweep */
+ *   sample_weights (1)       f64 weights: fixed-point form and scale from a sample, verified by the root sweep */
 int coupe_b200_set_option(coupe_b200_ctx *ctx, const char *name, int64_t value);
 
 /* Library / build identification string. */

@@ -344,6 +344,24 @@ def test_edge_cases(cb, oracle):
     assert np.array_equal(part.cpu().numpy().astype(np.uint64), oracle.rcb(pts, w[1:].copy(), 7, 0.05))
 
 
+def test_iter_count_limits(cb, oracle):
+    """Up to 2^24 parts (most of them empty here); beyond that COUPE_ERR_ALLOC, not a crash (include/coupe.h)."""
+    rng = np.random.default_rng(8)
+    n = 30_000
+    pts = rng.random((n, 2))
+    w = rng.integers(1, 10, n).astype(np.int64)
+    for iters in (21, 24):
+        got = run_device(cb, pts, w, iters, 0.05)
+        assert np.array_equal(got, oracle.rcb(pts, w, iters, 0.05))
+    with pytest.raises(cb.BackendError) as e:
+        run_device(cb, pts, w, 25, 0.05)
+    assert e.value.code == 1  # COUPE_ERR_ALLOC
+    part = np.full(n, 7, dtype=np.uint64)
+    with pytest.raises(cb.BackendError) as e:
+        cb.Rcb(40, 0.05).partition(part, (pts, w))
+    assert e.value.code == 1 and (part == 7).all()
+
+
 def test_carry_free_path_for_small_integer_weights(cb, oracle):
     """Integer weights with (largest weight) x (points per block) < 2^32 take the sweeps' carry-free adds;
     larger or negative ones the two-word path.  Same ids either way."""

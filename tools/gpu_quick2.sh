@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python tools/quick_bench.py --n 125000000 --w f64 --dist gauss --reps 3 --opt time_sweeps=2 2>&1 | tail -16
+timeout 300 python tools/quick_bench.py --n 125000000 --w f64 --dist gauss --reps 3 --opt time_sweeps=3 2>&1 | tail -16
 timeout 300 python bench.py --no-cpu-baseline --steps 5 > gpurun_out/bench_quick.json 2>/dev/null
 python - <<'PY'
 import json
