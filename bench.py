@@ -652,6 +652,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_total * e2e_steps / float(e2e_s.item()) / 1e6
+    # the same call on plain (pageable) memory, what a C or Rust host of the reference passes
+    e2e_pageable = None
+    if world == 1:
+        pg_pts, pg_part = np.array(np_pts, copy=True), np.empty_like(np_part)
+        pg_w = np_w if wconst else np.array(np_w, copy=True)
+        host_algo.partition(pg_part, (pg_pts, pg_w))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_algo.partition(pg_part, (pg_pts, pg_w))
+        e2e_pageable = {"value": n_total * e2e_steps / (time.perf_counter() - t0) / 1e6, "unit": UNIT,
+                        "ids_equal_device_path": bool(np.array_equal(pg_part, dev_ids)),
+                        "memory": "numpy arrays in pageable memory"}
+        del pg_pts, pg_part, pg_w
 
     if rank != 0:
         if world > 1:
@@ -755,6 +768,7 @@ def run_ours(args):
                          "coupe_b200_rcb_host / _rib_host (C ABI, include/coupe_b200.h) on each rank's pinned host shard"),
                 "bytes_note": "bytes of the caller's arrays (AoS f64 points, weights, usize ids); the library narrows the "
                               "points on the host and moves fewer bytes over PCIe (DESIGN.md, host path)"},
+        "e2e_pageable": e2e_pageable,
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -24,7 +24,9 @@ COUPE_B200_H_SYMBOLS = ["coupe_b200_ctx_create", "coupe_b200_ctx_destroy", "coup
                         "coupe_b200_ctx_init_comm", "coupe_b200_rcb_device", "coupe_b200_rib_device",
                         "coupe_b200_rcb_host", "coupe_b200_rib_host", "coupe_b200_host_release",
                         "coupe_b200_last_stats", "coupe_b200_last_sweep_times", "coupe_b200_last_trace", "coupe_b200_reserve",
-                        "coupe_b200_set_option", "coupe_b200_version"]
+                        "coupe_b200_set_option", "coupe_b200_version", "coupe_b200_group_create",
+                        "coupe_b200_group_destroy", "coupe_b200_group_size", "coupe_b200_group_ctx",
+                        "coupe_b200_rcb_host_group", "coupe_b200_rib_host_group"]
 # include/coupe_b200_tools.h
 COUPE_B200_TOOLS_H_SYMBOLS = ["coupe_b200_barycentres_device", "coupe_b200_weight_linear_device",
                               "coupe_b200_linear_alpha", "coupe_b200_weight_spike_device",
@@ -99,6 +101,18 @@ def lib():
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int,
                       C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]
     for f in (L.coupe_b200_rcb_host, L.coupe_b200_rib_host):
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                      C.c_void_p, C.c_size_t, C.c_double]
+    L.coupe_b200_group_create.restype = C.c_int
+    L.coupe_b200_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]
+    L.coupe_b200_group_destroy.restype = None
+    L.coupe_b200_group_destroy.argtypes = [C.c_void_p]
+    L.coupe_b200_group_size.restype = C.c_int
+    L.coupe_b200_group_size.argtypes = [C.c_void_p]
+    L.coupe_b200_group_ctx.restype = C.c_void_p
+    L.coupe_b200_group_ctx.argtypes = [C.c_void_p, C.c_int]
+    for f in (L.coupe_b200_rcb_host_group, L.coupe_b200_rib_host_group):
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                       C.c_void_p, C.c_size_t, C.c_double]

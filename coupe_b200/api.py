@@ -55,17 +55,28 @@ class Context:
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
+        self._owned = True
         err = _lib.lib().coupe_b200_ctx_create(C.byref(self._h), int(device))
         if err != 0:
             raise BackendError(err)
         self.device = int(device)
         self.rank, self.world = 0, 1
 
+    @classmethod
+    def _borrowed(cls, handle, rank: int, world: int):
+        """A context owned by a Group."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(handle)
+        self._owned = False
+        self.device = _lib.lib().coupe_b200_ctx_device(self._h)
+        self.rank, self.world = rank, world
+        return self
+
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             _lib.lib().coupe_b200_host_release(self._h)
             _lib.lib().coupe_b200_ctx_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -113,6 +124,38 @@ class Context:
         if err != 0:
             raise BackendError(err)
         self.rank, self.world = int(rank), int(world)
+
+
+class Group:
+    """Several GPUs of the box in ONE process (coupe_b200_group_create): `Rcb(..., context=group)` on host
+    arrays shards them over the devices.  `devices`: CUDA ordinals, or None for all of them."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        arr = None
+        n = 0
+        if devices is not None:
+            n = len(devices)
+            arr = (C.c_int * n)(*[int(d) for d in devices])
+        err = _lib.lib().coupe_b200_group_create(C.byref(self._h), arr, n)
+        if err != 0:
+            raise BackendError(err)
+        self.size = _lib.lib().coupe_b200_group_size(self._h)
+        self.contexts = [Context._borrowed(_lib.lib().coupe_b200_group_ctx(self._h, i), i, self.size)
+                         for i in range(self.size)]
+
+    def close(self):
+        if self._h:
+            for c in self.contexts:
+                c.close()
+            _lib.lib().coupe_b200_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default_ctx: dict[int, Context] = {}
@@ -192,8 +235,11 @@ def _host_call(rib: bool, ctx, part_ids, points, weights, iter_count, tolerance)
         raise InputLenMismatch(part_ids.shape[0], wlen)
     if n != part_ids.shape[0]:
         raise InputLenMismatch(part_ids.shape[0], n)
-    if ctx is not None:  # explicit context: the slice-level entry point a language binding uses
-        fn = L.coupe_b200_rib_host if rib else L.coupe_b200_rcb_host
+    if ctx is not None:  # explicit context (or group of GPUs): the slice-level entry point a language binding uses
+        if isinstance(ctx, Group):
+            fn = L.coupe_b200_rib_host_group if rib else L.coupe_b200_rcb_host_group
+        else:
+            fn = L.coupe_b200_rib_host if rib else L.coupe_b200_rcb_host
         err = fn(ctx._h, part_ids.ctypes.data, dim, n, pts.ctypes.data, tag,
                  None if const else w.ctypes.data, w.ctypes.data if const else None, int(iter_count),
                  float(tolerance))
@@ -222,7 +268,7 @@ class Rcb:
 
     iter_count: int = 0
     tolerance: float = 0.0
-    context: Context | None = None
+    context: "Context | Group | None" = None
 
     def partition(self, part_ids, data):
         points, weights = data
@@ -238,7 +284,7 @@ class Rib:
 
     iter_count: int = 0
     tolerance: float = 0.0
-    context: Context | None = None
+    context: "Context | Group | None" = None
 
     def partition(self, part_ids, data):
         points, weights = data

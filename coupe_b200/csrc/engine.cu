@@ -16,6 +16,7 @@
 
 #include "../../include/coupe.h"
 #include "../../include/coupe_b200.h"
+#include "engine_internal.h"
 #include "rcb_kernels.cuh"
 
 namespace {
@@ -61,6 +62,7 @@ struct NcclApi {
   void *handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -75,6 +77,7 @@ struct NcclApi {
     if (!handle) return false;
     GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommInitAll = (decltype(CommInitAll))dlsym(handle, "ncclCommInitAll");
     AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
     CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
     AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
@@ -216,6 +219,7 @@ struct coupe_b200_ctx {
   size_t max_smem = 0;
   std::mutex mu;
   // scratch
+  Buf host_w, host_ids, host_pts;  // host path: device copies of the caller's weights / (RIB) points, compact ids
   Buf xcols, ids, w32, node_rt, rfast, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
       tsp_a, tsp_b, nsh_a, nsh_b, target, rtable, gp,
       tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
@@ -228,6 +232,7 @@ struct coupe_b200_ctx {
   int rank = 0, world = 1;
   // peer-memory exchange of the level histograms (rcb_kernels.cuh: Xchg); off -> NCCL all-reduces
   bool xchg_ok = false;
+  bool xchg_local = false;  // the peers' buffers belong to contexts of this process (no IPC handles to close)
   int use_xchg_opt = 1;
   unsigned char *xchg_peer[XCHG_MAX_WORLD] = {nullptr};  // [rank] is this rank's own cudaMalloc'ed buffer
   unsigned int *xchg_aux = nullptr;                       // {ticket, error}
@@ -389,7 +394,8 @@ struct Run {
 
 int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, uintptr_t dim,
              uintptr_t n, const double *pts, int wtype, const void *w_dev, const void *wconst_host,
-             uintptr_t iter_count, double tolerance) {
+             uintptr_t iter_count, double tolerance, const cb_engine::Prefilled *pre = nullptr,
+             int *compact_id_bytes = nullptr) {
   if (dim != 2 && dim != 3) return COUPE_ERR_BAD_DIMENSION;
   if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
   if (n > 0 && !w_dev && !wconst_host) return COUPE_ERR_CRASH;
@@ -473,8 +479,11 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
                          (wtype == WT_I32 && L > 1 && w_dev && ((uintptr_t)w_dev % 16) != 0));
   if (narrow_w) c->w32.ensure(npad * sizeof(int));
   if (n_global == 0) return COUPE_ERR_OK;  // BoundingBox::from_points -> None (:685-688)
+  const int id_bytes = L <= 16 ? 2 : 4;  // compact ids of the host path
+  if (compact_id_bytes) *compact_id_bytes = id_bytes;
   if (L == 0) {                            // iter_count == 0: every id is 0
-    if (n) CU(cudaMemsetAsync(part_dev, 0, n * sizeof(uint64_t), st));
+    if (n && compact_id_bytes) CU(cudaMemsetAsync(c->host_ids.p, 0, n * id_bytes, st));
+    else if (n) CU(cudaMemsetAsync(part_dev, 0, n * sizeof(uint64_t), st));
     R.sync();
     return COUPE_ERR_OK;
   }
@@ -525,14 +534,23 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const double *wf = (wtype == WT_F64 && w_dev) ? static_cast<const double *>(w_dev) : nullptr;
     const int ws = c->sample_w_opt ? 1 : 0;
     const int pa = ((uintptr_t)pts % 16) == 0, wa = ((uintptr_t)w_dev % 16) == 0;
-    if (D == 2) {
+    if (pre) {
+      // host path: the columns were filled from the host (narrowed there), the box came with them
+      memcpy(c->h_pinned + 16, pre->bbox_keys, sizeof(pre->bbox_keys));
+      CU(cudaMemcpyAsync(gp->bbox_keys, c->h_pinned + 16, sizeof(pre->bbox_keys), cudaMemcpyHostToDevice, st));
+      if (wf && n) {
+        const size_t items = ws ? ((ngroups + 16383) / 16384) * 256 : ngroups;
+        wsample_kernel<<<std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 8, (items + 255) / 256)), 256, 0, st>>>(wf, n, gp, ws);
+        R.launched();
+      }
+    } else if (D == 2) {
       if (rib) narrow_kernel<2, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
       else narrow_kernel<2, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
     } else {
       if (rib) narrow_kernel<3, true><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
       else narrow_kernel<3, false><<<grid, 256, 0, st>>>(pts, n, x[0], x[1], x[2], rot, gp, wf, pa, wa, ws);
     }
-    R.launched();
+    if (!pre) R.launched();
     if (c->world > 1) {
       R.allreduce(gp->bbox_keys, 8, ncclUint32, ncclMin);
       // every statistic is kept as a maximum; decided on the GLOBAL "weights are an array" fact (empty shards)
@@ -785,10 +803,17 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const int grid = std::max(1, (int)std::min<size_t>((size_t)c->num_sms * 4, (ngroups + 511) / 512));
     unsigned long long *out = reinterpret_cast<unsigned long long *>(part_dev);
     const int out_vec = ((uintptr_t)part_dev % 32) == 0 ? 2 : ((uintptr_t)part_dev % 16) == 0 ? 1 : 0;
-    if (idx16)
-      launch_pdl(emit_kernel<uint16_t>, grid, 512, 0, st, n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
-    else
-      launch_pdl(emit_kernel<uint32_t>, grid, 512, 0, st, n, ids, x[(L - 1) % D], tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+    const float *xl = x[(L - 1) % D];
+    if (compact_id_bytes && id_bytes == 2) {  // (L <= 16 implies 16-bit idx words)
+      launch_pdl(emit_kernel<uint16_t, uint16_t>, grid, 512, 0, st, n, ids, xl, tab_cur, tsp_cur, klast, gp, c->host_ids.as<uint16_t>(), 0, guard);
+    } else if (compact_id_bytes) {
+      if (idx16) launch_pdl(emit_kernel<uint16_t, uint32_t>, grid, 512, 0, st, n, ids, xl, tab_cur, tsp_cur, klast, gp, c->host_ids.as<uint32_t>(), 0, guard);
+      else launch_pdl(emit_kernel<uint32_t, uint32_t>, grid, 512, 0, st, n, ids, xl, tab_cur, tsp_cur, klast, gp, c->host_ids.as<uint32_t>(), 0, guard);
+    } else if (idx16) {
+      launch_pdl(emit_kernel<uint16_t, unsigned long long>, grid, 512, 0, st, n, ids, xl, tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+    } else {
+      launch_pdl(emit_kernel<uint32_t, unsigned long long>, grid, 512, 0, st, n, ids, xl, tab_cur, tsp_cur, klast, gp, out, out_vec, guard);
+    }
     R.launched();
   };
 
@@ -903,14 +928,12 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   return COUPE_ERR_OK;
 }
 
-int guarded(coupe_b200_ctx *c, bool rib, void *stream, uint64_t *part_dev, uintptr_t dim, uintptr_t n,
-            const double *pts, int wtype, const void *w_dev, const void *wconst_host,
-            uintptr_t iter_count, double tolerance) {
-  if (!c) return COUPE_ERR_CRASH;
-  std::lock_guard<std::mutex> lock(c->mu);
+int guarded_locked(coupe_b200_ctx *c, bool rib, void *stream, uint64_t *part_dev, uintptr_t dim, uintptr_t n,
+                   const double *pts, int wtype, const void *w_dev, const void *wconst_host,
+                   uintptr_t iter_count, double tolerance, const cb_engine::Prefilled *pre, int *compact_id_bytes) {
   try {
     return run_impl(c, rib, static_cast<cudaStream_t>(stream), part_dev, dim, n, pts, wtype, w_dev,
-                    wconst_host, iter_count, tolerance);
+                    wconst_host, iter_count, tolerance, pre, compact_id_bytes);
   } catch (const CudaFail &f) {
     fprintf(stderr, "coupe_b200: CUDA error %s at %s\n", cudaGetErrorString(f.err), f.what);
     cudaGetLastError();
@@ -923,6 +946,15 @@ int guarded(coupe_b200_ctx *c, bool rib, void *stream, uint64_t *part_dev, uintp
   } catch (...) {
     return COUPE_ERR_CRASH;
   }
+}
+
+int guarded(coupe_b200_ctx *c, bool rib, void *stream, uint64_t *part_dev, uintptr_t dim, uintptr_t n,
+            const double *pts, int wtype, const void *w_dev, const void *wconst_host,
+            uintptr_t iter_count, double tolerance) {
+  if (!c) return COUPE_ERR_CRASH;
+  std::lock_guard<std::mutex> lock(c->mu);
+  return guarded_locked(c, rib, stream, part_dev, dim, n, pts, wtype, w_dev, wconst_host, iter_count, tolerance,
+                        nullptr, nullptr);
 }
 
 // Peer-memory exchange: allocate this rank's buffer, share its IPC handle with the other ranks
@@ -1009,6 +1041,48 @@ void setup_xchg(coupe_b200_ctx *c) {
 
 }  // namespace
 
+namespace cb_engine {
+
+void (*on_destroy)(coupe_b200_ctx *c) = nullptr;
+void release_host_buffers(coupe_b200_ctx *c) {
+  for (Buf *b : {&c->host_w, &c->host_ids, &c->host_pts}) b->release();
+}
+void lock(coupe_b200_ctx *c) { c->mu.lock(); }
+void unlock(coupe_b200_ctx *c) { c->mu.unlock(); }
+int device_of(const coupe_b200_ctx *c) { return c->device; }
+int rank_of(const coupe_b200_ctx *c) { return c->rank; }
+int world_of(const coupe_b200_ctx *c) { return c->world; }
+
+int host_columns(coupe_b200_ctx *c, size_t n, size_t dim, size_t wbytes, bool raw_points, size_t iter_count,
+                 HostColumns *out) {
+  try {
+    CU(cudaSetDevice(c->device));
+    const size_t npad = ((n + 3) / 4) * 4 + 4;
+    c->xcols.ensure(npad * sizeof(float) * 3);
+    if (wbytes) c->host_w.ensure(npad * wbytes);
+    c->host_ids.ensure(npad * (iter_count <= 16 ? 2 : 4));
+    if (raw_points) c->host_pts.ensure(npad * dim * sizeof(double));
+    out->npad = npad;
+    for (int d = 0; d < 3; ++d) out->x[d] = c->xcols.as<float>() + (size_t)d * npad;
+    out->w = wbytes ? c->host_w.p : nullptr;
+    out->ids_compact = c->host_ids.p;
+    out->pts_raw = raw_points ? c->host_pts.as<double>() : nullptr;
+    return COUPE_ERR_OK;
+  } catch (const CudaFail &f) {
+    cudaGetLastError();
+    return f.err == cudaErrorMemoryAllocation ? COUPE_ERR_ALLOC : COUPE_ERR_CRASH;
+  }
+}
+
+int run_locked(coupe_b200_ctx *c, bool rib, cudaStream_t st, const Prefilled *pre, int *id_bytes, uintptr_t dim,
+               uintptr_t n, const double *points_dev, int wtype, const void *weights_dev, const void *wconst_host,
+               uintptr_t iter_count, double tolerance) {
+  return guarded_locked(c, rib, st, nullptr, dim, n, points_dev, wtype, weights_dev, wconst_host, iter_count,
+                        tolerance, pre, id_bytes);
+}
+
+}  // namespace cb_engine
+
 extern "C" {
 
 int coupe_b200_ctx_create(coupe_b200_ctx **out, int device) {
@@ -1048,18 +1122,19 @@ int coupe_b200_ctx_create(coupe_b200_ctx **out, int device) {
 
 void coupe_b200_ctx_destroy(coupe_b200_ctx *c) {
   if (!c) return;
+  if (cb_engine::on_destroy) cb_engine::on_destroy(c);  // the host path's pinned buffers and streams (ffi.cu)
   cudaSetDevice(c->device);
   if (c->xchg_ok) {
     cudaDeviceSynchronize();
     for (int r = 0; r < c->world; ++r) {
       if (!c->xchg_peer[r]) continue;
       if (r == c->rank) cudaFree(c->xchg_peer[r]);
-      else cudaIpcCloseMemHandle(c->xchg_peer[r]);
+      else if (!c->xchg_local) cudaIpcCloseMemHandle(c->xchg_peer[r]);
     }
     if (c->xchg_aux) cudaFree(c->xchg_aux);
   }
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (Buf *b : {&c->xcols, &c->ids, &c->w32, &c->node_rt, &c->rfast, &c->tsp_a, &c->tsp_b, &c->nsh_a, &c->nsh_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
+  for (Buf *b : {&c->host_w, &c->host_ids, &c->host_pts, &c->xcols, &c->ids, &c->w32, &c->node_rt, &c->rfast, &c->tsp_a, &c->tsp_b, &c->nsh_a, &c->nsh_b, &c->target, &c->part_w, &c->part_min, &c->hist_w, &c->hist_min, &c->nodes_a,
                  &c->nodes_b, &c->table_a, &c->table_b, &c->thi_a, &c->thi_b, &c->rtable, &c->gp, &c->tr_visited,
                  &c->tr_split, &c->tr_wl, &c->tr_sum, &c->tr_iters, &c->mom_partial})
     b->release();
@@ -1095,6 +1170,111 @@ int coupe_b200_ctx_init_comm(coupe_b200_ctx *c, const void *unique_id128, int ra
   c->world = world;
   setup_xchg(c);  // optional: without it the histograms go through NCCL all-reduces
   return COUPE_ERR_OK;
+}
+
+// One process, several GPUs: one context per device, ranks of a communicator made with
+// ncclCommInitAll; the exchange buffers are mapped with plain peer access.
+int coupe_b200_group_create(coupe_b200_group **out, const int *devices, int ndev) {
+  if (!out) return COUPE_ERR_CRASH;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return COUPE_ERR_CRASH;  // no CPU fallback
+  }
+  std::vector<int> devs;
+  if (ndev <= 0 || !devices) {
+    for (int d = 0; d < count; ++d) devs.push_back(d);
+  } else {
+    for (int i = 0; i < ndev; ++i) {
+      if (devices[i] < 0 || devices[i] >= count) return COUPE_ERR_CRASH;
+      for (int j = 0; j < i; ++j)
+        if (devices[j] == devices[i]) return COUPE_ERR_CRASH;
+      devs.push_back(devices[i]);
+    }
+  }
+  const int world = (int)devs.size();
+  if (world > XCHG_MAX_WORLD) return COUPE_ERR_CRASH;
+  coupe_b200_group *g = new (std::nothrow) coupe_b200_group();
+  if (!g) return COUPE_ERR_ALLOC;
+  auto fail = [&](int err) {
+    for (coupe_b200_ctx *c : g->ctx) coupe_b200_ctx_destroy(c);
+    delete g;
+    return err;
+  };
+  for (int d : devs) {
+    coupe_b200_ctx *c = nullptr;
+    const int err = coupe_b200_ctx_create(&c, d);
+    if (err != COUPE_ERR_OK) return fail(err);
+    g->ctx.push_back(c);
+  }
+  if (world > 1) {
+    if (!g_nccl.load() || !g_nccl.CommInitAll) return fail(COUPE_ERR_CRASH);
+    std::vector<ncclComm_t> comms(world);
+    if (g_nccl.CommInitAll(comms.data(), world, devs.data()) != ncclSuccess) return fail(COUPE_ERR_CRASH);
+    for (int r = 0; r < world; ++r) {
+      g->ctx[r]->comm = comms[r];
+      g->ctx[r]->rank = r;
+      g->ctx[r]->world = world;
+    }
+    // peer-memory exchange: every device maps every other one's buffer directly
+    bool ok = true;
+    if (const char *e = getenv("COUPE_B200_NO_PEER_EXCHANGE"))
+      if (*e && *e != '0') ok = false;
+    for (int a = 0; a < world && ok; ++a)
+      for (int b = 0; b < world && ok; ++b) {
+        if (a == b) continue;
+        int can = 0;
+        ok = cudaDeviceCanAccessPeer(&can, devs[a], devs[b]) == cudaSuccess && can;
+        if (!ok) break;
+        ok = cudaSetDevice(devs[a]) == cudaSuccess;
+        const cudaError_t e = ok ? cudaDeviceEnablePeerAccess(devs[b], 0) : cudaErrorUnknown;
+        ok = ok && (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+        cudaGetLastError();
+      }
+    std::vector<void *> bufs(world, nullptr), aux(world, nullptr);
+    const size_t bytes = xchg_bytes(world);
+    for (int r = 0; r < world && ok; ++r)
+      ok = cudaSetDevice(devs[r]) == cudaSuccess && cudaMalloc(&bufs[r], bytes) == cudaSuccess &&
+           cudaMemset(bufs[r], 0, bytes) == cudaSuccess && cudaMalloc(&aux[r], 64) == cudaSuccess &&
+           cudaMemset(aux[r], 0, 64) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+    if (ok) {
+      for (int r = 0; r < world; ++r) {
+        coupe_b200_ctx *c = g->ctx[r];
+        for (int p = 0; p < world; ++p) c->xchg_peer[p] = static_cast<unsigned char *>(bufs[p]);
+        c->xchg_aux = static_cast<unsigned int *>(aux[r]);
+        c->xchg_ok = true;
+        c->xchg_local = true;
+      }
+    } else {
+      cudaGetLastError();
+      for (int r = 0; r < world; ++r) {
+        cudaSetDevice(devs[r]);
+        if (bufs[r]) cudaFree(bufs[r]);
+        if (aux[r]) cudaFree(aux[r]);
+      }
+      fprintf(stderr, "coupe_b200: peer-memory exchange unavailable in this process, using NCCL all-reduces\n");
+    }
+  }
+  *out = g;
+  return COUPE_ERR_OK;
+}
+
+void coupe_b200_group_destroy(coupe_b200_group *g) {
+  if (!g) return;
+  // every context frees its own exchange buffer; the peers' pointers are plain aliases
+  for (coupe_b200_ctx *c : g->ctx) {
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+  }
+  for (coupe_b200_ctx *c : g->ctx) coupe_b200_ctx_destroy(c);
+  delete g;
+}
+
+int coupe_b200_group_size(const coupe_b200_group *g) { return g ? (int)g->ctx.size() : 0; }
+
+coupe_b200_ctx *coupe_b200_group_ctx(coupe_b200_group *g, int i) {
+  return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[i] : nullptr;
 }
 
 int coupe_b200_rcb_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev, uintptr_t dim,

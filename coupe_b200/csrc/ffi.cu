@@ -4,12 +4,17 @@
 // (Array / Constant / Fn data sets): same names, argument meaning and error
 // codes; the work itself runs on the GPU (no CPU fallback).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <limits>
 #include <new>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
@@ -17,6 +22,8 @@
 
 #include "../../include/coupe.h"
 #include "../../include/coupe_b200.h"
+#include "engine_internal.h"
+#include "host_simd.h"
 
 struct coupe_data {
   enum Kind { ARRAY, CONSTANT, FN } kind;
@@ -28,32 +35,13 @@ struct coupe_data {
 
 namespace {
 
-std::mutex g_mu;
+using cb_engine::HostColumns;
+
+std::mutex g_mu;  // the default context and the per-context host state below (not the calls themselves)
 coupe_b200_ctx *g_ctx = nullptr;
 
-struct DevBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-  bool ensure(size_t bytes) {
-    if (bytes <= cap) return true;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    cap = bytes;
-    return true;
-  }
-};
-// Device staging of the host entry points, one set per context.
-struct Staging {
-  DevBuf pts, w, part;
-};
-std::map<coupe_b200_ctx *, Staging> g_staging;
-
 coupe_b200_ctx *default_ctx() {
+  std::lock_guard<std::mutex> lock(g_mu);
   if (g_ctx) return g_ctx;
   int dev = 0;
   if (const char *e = getenv("COUPE_B200_DEVICE")) dev = atoi(e);
@@ -62,6 +50,19 @@ coupe_b200_ctx *default_ctx() {
 }
 
 size_t type_size(coupe_type t) { return t == COUPE_INT ? 4 : 8; }
+
+unsigned host_threads() {
+  static const unsigned n = [] {
+    if (const char *e = getenv("COUPE_B200_HOST_THREADS"))
+      if (atoi(e) > 0) return (unsigned)std::min(64, atoi(e));
+    cpu_set_t set;
+    unsigned c = 0;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) c = (unsigned)CPU_COUNT(&set);
+    if (c == 0) c = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(c, 32u));
+  }();
+  return n;
+}
 
 // Materialise a Constant or Fn data set into `out` (elem bytes per element);
 // Fn callbacks are evaluated from several threads, as the reference does with rayon.
@@ -73,7 +74,7 @@ bool materialise(const coupe_data *d, size_t elem, std::vector<unsigned char> &o
   }
   unsigned char *o = out.data();
   const size_t n = d->len;
-  unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+  unsigned nt = host_threads();
   if (n < 65536) nt = 1;
   auto work = [&](size_t lo, size_t hi) {
     if (d->kind == coupe_data::CONSTANT) {
@@ -96,39 +97,69 @@ bool materialise(const coupe_data *d, size_t elem, std::vector<unsigned char> &o
   return true;
 }
 
-// ---- host <-> device copies of caller-owned arrays ------------------------------------------
-// Callers of the reference hand over plain (pageable) memory.  cudaMemcpy on pageable memory is a
-// single-threaded bounce through the driver's staging buffer (10-20 GB/s); here several host
-// threads each own two pinned buffers and a stream and move alternate chunks: memcpy into (out
-// of) pinned memory overlaps the DMA of the other buffer and the threads together keep the link
-// busy.  Memory the caller has pinned itself (cudaHostAlloc / cudaHostRegister) goes straight
-// through one cudaMemcpy.
-constexpr size_t STAGE_CHUNK = 8u << 20;  // bytes per pinned buffer
-constexpr unsigned STAGE_THREADS = 8;
+// ---- the host path: caller-owned host arrays <-> the engine's device columns --------------------
+// What crosses PCIe is what the kernels need, not what the caller holds:
+//   up:   the coordinates NARROWED to f32 by host threads (RNE, bit-identical to narrow_kernel) and laid
+//         out as the engine's SoA columns: 4 D bytes per point instead of 8 D; the root bounding box comes
+//         from the same pass over the caller's array.  Weights as supplied (4 or 8 bytes).
+//         RIB: the rotation precedes the narrowing (recursive_bisection.rs:848), so the f64 points go up.
+//   down: compact part ids (2 bytes up to 2^16 parts, else 4), widened to `usize` by the host threads
+//         that drain the copy.
+// Host threads ("lanes") each own pinned buffers and a stream: while one buffer is in flight the lane
+// fills the next; chunks are handed out by an atomic counter.  Memory the caller has pinned itself
+// (cudaHostAlloc / cudaHostRegister) is copied by the DMA engines straight from where it lies.
+constexpr size_t CHUNK_POINTS = (size_t)1 << 18;
+constexpr int LANE_BUFS = 2;
+constexpr size_t LANE_BUF_BYTES = CHUNK_POINTS * 32;  // a chunk of raw 3-D f64 points + 8-byte weights, the largest use
 
-struct StageLane {
-  void *buf[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
+struct Lane {
+  void *buf[LANE_BUFS] = {nullptr, nullptr};
+  cudaEvent_t done[LANE_BUFS] = {nullptr, nullptr};
   cudaStream_t stream = nullptr;
-  bool ok() const { return buf[0] && buf[1] && done[0] && done[1] && stream; }
 };
-StageLane g_lanes[STAGE_THREADS];
-bool g_lanes_ready = false;
-int g_lanes_device = -1;  // the streams belong to the device of the first call; other devices use plain copies
+struct HostState {  // per context, on the context's device
+  std::vector<Lane> lanes;
+  bool ready = false, failed = false;
+};
+std::map<coupe_b200_ctx *, HostState> g_host;
 
-bool ensure_lanes(int device) {
-  if (g_lanes_ready) return g_lanes_device == device;
-  if (g_lanes_device >= 0) return false;  // an earlier attempt failed half way
-  g_lanes_device = device;
-  for (StageLane &l : g_lanes) {
-    for (int b = 0; b < 2; ++b) {
-      if (cudaHostAlloc(&l.buf[b], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) return false;
-      if (cudaEventCreateWithFlags(&l.done[b], cudaEventDisableTiming) != cudaSuccess) return false;
+void free_lanes(HostState &hs) {
+  for (Lane &l : hs.lanes) {
+    for (int b = 0; b < LANE_BUFS; ++b) {
+      if (l.buf[b]) cudaFreeHost(l.buf[b]);
+      if (l.done[b]) cudaEventDestroy(l.done[b]);
     }
-    if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (l.stream) cudaStreamDestroy(l.stream);
   }
-  g_lanes_ready = true;
-  return true;
+  hs.lanes.clear();
+  hs.ready = false;
+}
+
+// Context locked, its device current.
+HostState *host_state(coupe_b200_ctx *ctx, unsigned want_lanes) {
+  HostState *hs;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    hs = &g_host[ctx];
+  }
+  if (hs->ready && hs->lanes.size() >= want_lanes) return hs;
+  if (hs->failed) return nullptr;
+  free_lanes(*hs);
+  hs->lanes.resize(want_lanes);
+  for (Lane &l : hs->lanes) {
+    bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int b = 0; b < LANE_BUFS && ok; ++b)
+      ok = cudaHostAlloc(&l.buf[b], LANE_BUF_BYTES, cudaHostAllocDefault) == cudaSuccess &&
+           cudaEventCreateWithFlags(&l.done[b], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      free_lanes(*hs);
+      hs->failed = true;
+      return nullptr;
+    }
+  }
+  hs->ready = true;
+  return hs;
 }
 
 bool is_pinned(const void *p) {
@@ -140,80 +171,223 @@ bool is_pinned(const void *p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// to_device: host -> dev, else dev -> host.  Returns false on any CUDA failure.
-bool staged_copy(void *dev, void *host, size_t bytes, bool to_device, int device) {
-  if (bytes == 0) return true;
-  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-  static const bool no_staging = [] { const char *e = getenv("COUPE_B200_NO_STAGING"); return e && *e && *e != '0'; }();
-  if (no_staging || bytes < 4 * STAGE_CHUNK || is_pinned(host) || !ensure_lanes(device))
-    return cudaMemcpy(to_device ? dev : host, to_device ? host : dev, bytes, kind) == cudaSuccess;
-  const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
-  const unsigned nt = (unsigned)std::min<size_t>(STAGE_THREADS, nchunks);
-  bool ok[STAGE_THREADS];
-  auto work = [&](unsigned t) {
-    ok[t] = cudaSetDevice(device) == cudaSuccess;
-    StageLane &l = g_lanes[t];
-    int b = 0;
-    size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
-    for (size_t c = t; c < nchunks && ok[t]; c += nt, b ^= 1) {
-      const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
-      // the buffer's previous transfer must be over (and, device -> host, copied out) before it is reused
-      if (pending_len[b]) {
-        ok[t] = cudaEventSynchronize(l.done[b]) == cudaSuccess;
-        if (!to_device) memcpy(static_cast<char *>(host) + pending_off[b], l.buf[b], pending_len[b]);
-      }
-      if (to_device) {
-        memcpy(l.buf[b], static_cast<const char *>(host) + off, len);
-        ok[t] = ok[t] && cudaMemcpyAsync(static_cast<char *>(dev) + off, l.buf[b], len, kind, l.stream) == cudaSuccess;
-      } else {
-        ok[t] = ok[t] && cudaMemcpyAsync(l.buf[b], static_cast<const char *>(dev) + off, len, kind, l.stream) == cudaSuccess;
-      }
-      ok[t] = ok[t] && cudaEventRecord(l.done[b], l.stream) == cudaSuccess;
-      pending_off[b] = off;
-      pending_len[b] = len;
-    }
-    for (int q = 0; q < 2; ++q)
-      if (pending_len[q]) {
-        ok[t] = cudaEventSynchronize(l.done[q]) == cudaSuccess && ok[t];
-        if (!to_device) memcpy(static_cast<char *>(host) + pending_off[q], l.buf[q], pending_len[q]);
-      }
-  };
+inline uint32_t f2key_host(float f) {  // rcb_kernels.cuh: f2key
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Runs fn(lane index) on `nt` threads (the calling one included); false if any returned false.
+template <class F>
+bool on_lanes(unsigned nt, F fn) {
+  std::vector<char> ok(nt, 0);
   std::vector<std::thread> th;
-  for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-  work(0);
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back([&, t] { ok[t] = fn(t) ? 1 : 0; });
+  ok[0] = fn(0) ? 1 : 0;
   for (auto &x : th) x.join();
   bool all = true;
-  for (unsigned t = 0; t < nt; ++t) all = all && ok[t];
+  for (char o : ok) all = all && o;
   if (!all) cudaGetLastError();
   return all;
 }
 
-// Host arrays in, host part ids out: copy to the device, run the CUDA path, copy back.
-// Caller holds g_mu.
+// Host arrays in, host part ids out.  Returns a coupe_err.
 int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dimension, uintptr_t n,
              const double *pts_host, int wtype, const void *w_host, const void *w_const,
-             uintptr_t iter_count, double tolerance) {
+             uintptr_t iter_count, double tolerance, unsigned lane_budget = 0) {
   if (dimension != 2 && dimension != 3) return COUPE_ERR_BAD_DIMENSION;
   if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
-  if (n == 0) return COUPE_ERR_OK;  // nothing to write (recursive_bisection.rs:685-688)
-  if (!pts_host || !partition || (!w_host && !w_const)) return COUPE_ERR_CRASH;
-  Staging &sg = g_staging[ctx];
-  const size_t pelem = dimension * sizeof(double);
-  const size_t welem = wtype == COUPE_INT ? 4 : 8;
-  if (!sg.pts.ensure(n * pelem) || !sg.part.ensure(n * sizeof(uint64_t))) return COUPE_ERR_ALLOC;
-  if (w_host && !sg.w.ensure(n * welem)) return COUPE_ERR_ALLOC;
-  const int device = coupe_b200_ctx_device(ctx);
+  const bool single = cb_engine::world_of(ctx) <= 1;
+  if (n == 0 && single) return COUPE_ERR_OK;  // nothing to write (recursive_bisection.rs:685-688)
+  if (n > 0 && (!pts_host || !partition || (!w_host && !w_const))) return COUPE_ERR_CRASH;
+  struct Locked {
+    coupe_b200_ctx *c;
+    explicit Locked(coupe_b200_ctx *c) : c(c) { cb_engine::lock(c); }
+    ~Locked() { cb_engine::unlock(c); }
+  } locked(ctx);
+  const int device = cb_engine::device_of(ctx);
   if (cudaSetDevice(device) != cudaSuccess) return COUPE_ERR_CRASH;
-  if (!staged_copy(sg.pts.p, const_cast<double *>(pts_host), n * pelem, true, device)) return COUPE_ERR_CRASH;
-  if (w_host && !staged_copy(sg.w.p, const_cast<void *>(w_host), n * welem, true, device)) return COUPE_ERR_CRASH;
-  auto fn = rib ? coupe_b200_rib_device : coupe_b200_rcb_device;
-  const int err = fn(ctx, nullptr, static_cast<uint64_t *>(sg.part.p), dimension, n,
-                     static_cast<const double *>(sg.pts.p), wtype, w_host ? sg.w.p : nullptr, w_const,
-                     iter_count, tolerance);
+  const int D = (int)dimension;
+  const size_t wb = w_host ? (wtype == COUPE_INT ? 4 : 8) : 0;
+  HostColumns cols{};
+  int err = cb_engine::host_columns(ctx, n, dimension, wb, rib, iter_count, &cols);
   if (err != COUPE_ERR_OK) return err;
+  const size_t nchunks = (n + CHUNK_POINTS - 1) / CHUNK_POINTS;
+  if (lane_budget == 0) lane_budget = host_threads();
+  const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(lane_budget, nchunks));
+  HostState *hs = host_state(ctx, lane_budget);
+  if (!hs) return COUPE_ERR_ALLOC;
+  const bool w_pinned = w_host && is_pinned(w_host);
+  const bool p_pinned = rib && n && is_pinned(pts_host);
+
+  static const bool timing = [] { const char *e = getenv("COUPE_B200_HOST_TIMING"); return e && *e && *e != '0'; }();
+  const auto t_start = std::chrono::steady_clock::now();
+  auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
+  // ---- up ----------------------------------------------------------------------------------------
+  std::vector<float> bmin((size_t)nt * 3, std::numeric_limits<float>::infinity());
+  std::vector<float> bmax((size_t)nt * 3, -std::numeric_limits<float>::infinity());
+  std::atomic<size_t> next{0};
+  auto upload = [&](unsigned t) -> bool {
+    if (cudaSetDevice(device) != cudaSuccess) return false;
+    Lane &l = hs->lanes[t];
+    bool pending[LANE_BUFS] = {false, false};
+    int b = 0;
+    bool ok = true;
+    for (size_t c; ok && (c = next.fetch_add(1)) < nchunks; b = (b + 1) % LANE_BUFS) {
+      const size_t lo = c * CHUNK_POINTS, hi = std::min<size_t>(n, lo + CHUNK_POINTS), m = hi - lo;
+      if (pending[b]) ok = cudaEventSynchronize(l.done[b]) == cudaSuccess;  // the buffer's previous copy is over
+      char *buf = static_cast<char *>(l.buf[b]);
+      size_t used = 0;
+      if (!rib) {
+        float *s = reinterpret_cast<float *>(buf);
+        if (D == 2) cb_host::narrow_chunk<2>(pts_host, lo, hi, s, m, &bmin[t * 3], &bmax[t * 3]);
+        else cb_host::narrow_chunk<3>(pts_host, lo, hi, s, m, &bmin[t * 3], &bmax[t * 3]);
+        for (int d = 0; d < D && ok; ++d)
+          ok = cudaMemcpyAsync(cols.x[d] + lo, s + (size_t)d * m, m * 4, cudaMemcpyHostToDevice, l.stream) == cudaSuccess;
+        used = (size_t)D * m * 4;
+      } else {  // RIB: the f64 points themselves
+        const size_t bytes = m * D * 8;
+        const char *src = reinterpret_cast<const char *>(pts_host + lo * D);
+        if (!p_pinned) {
+          memcpy(buf, src, bytes);
+          src = buf;
+          used = bytes;
+        }
+        ok = cudaMemcpyAsync(cols.pts_raw + lo * D, src, bytes, cudaMemcpyHostToDevice, l.stream) == cudaSuccess;
+      }
+      if (w_host && ok) {
+        const char *src = static_cast<const char *>(w_host) + lo * wb;
+        if (!w_pinned) {
+          used = (used + 15) & ~(size_t)15;
+          memcpy(buf + used, src, m * wb);
+          src = buf + used;
+        }
+        ok = cudaMemcpyAsync(static_cast<char *>(cols.w) + lo * wb, src, m * wb, cudaMemcpyHostToDevice, l.stream) == cudaSuccess;
+      }
+      ok = ok && cudaEventRecord(l.done[b], l.stream) == cudaSuccess;
+      pending[b] = true;
+    }
+    return cudaStreamSynchronize(l.stream) == cudaSuccess && ok;
+  };
+  if (n && !on_lanes(nt, upload)) return COUPE_ERR_CRASH;
+  cb_engine::Prefilled pre;
+  for (int k = 0; k < 8; ++k) pre.bbox_keys[k] = 0xFFFFFFFFu;
+  for (int d = 0; d < D; ++d) {
+    float mn = std::numeric_limits<float>::infinity(), mx = -std::numeric_limits<float>::infinity();
+    for (unsigned t = 0; t < nt; ++t) {
+      mn = bmin[t * 3 + d] < mn ? bmin[t * 3 + d] : mn;
+      mx = mx < bmax[t * 3 + d] ? bmax[t * 3 + d] : mx;
+    }
+    pre.bbox_keys[d] = f2key_host(mn);
+    pre.bbox_keys[4 + d] = ~f2key_host(mx);
+  }
+
+  const double ms_up = ms_since(t_start);
+  // ---- the CUDA path --------------------------------------------------------------------------------
+  int id_bytes = 0;
+  err = cb_engine::run_locked(ctx, rib, nullptr, rib ? nullptr : &pre, &id_bytes, dimension, n, cols.pts_raw, wtype,
+                              w_host ? cols.w : nullptr, w_const, iter_count, tolerance);
+  if (err != COUPE_ERR_OK) return err;
+
+  const double ms_run = ms_since(t_start) - ms_up;
+  // ---- down: compact ids, widened on the way out ----------------------------------------------------
   static_assert(sizeof(uintptr_t) == sizeof(uint64_t), "usize is 64 bit");
-  if (!staged_copy(sg.part.p, partition, n * sizeof(uint64_t), false, device)) return COUPE_ERR_CRASH;
+  next = 0;
+  auto download = [&](unsigned t) -> bool {
+    if (cudaSetDevice(device) != cudaSuccess) return false;
+    Lane &l = hs->lanes[t];
+    size_t plo[LANE_BUFS] = {0, 0}, pm[LANE_BUFS] = {0, 0};
+    bool ok = true;
+    auto widen = [&](int b) {
+      if (!pm[b]) return;
+      ok = cudaEventSynchronize(l.done[b]) == cudaSuccess && ok;
+      cb_host::widen_ids(l.buf[b], id_bytes, partition + plo[b], pm[b]);
+      pm[b] = 0;
+    };
+    int b = 0;
+    for (size_t c; ok && (c = next.fetch_add(1)) < nchunks; b = (b + 1) % LANE_BUFS) {
+      const size_t lo = c * CHUNK_POINTS, hi = std::min<size_t>(n, lo + CHUNK_POINTS), m = hi - lo;
+      widen(b);  // the buffer's previous chunk
+      ok = ok && cudaMemcpyAsync(l.buf[b], static_cast<const char *>(cols.ids_compact) + lo * id_bytes, m * id_bytes,
+                                 cudaMemcpyDeviceToHost, l.stream) == cudaSuccess &&
+           cudaEventRecord(l.done[b], l.stream) == cudaSuccess;
+      plo[b] = lo;
+      pm[b] = ok ? m : 0;
+    }
+    for (int q = 0; q < LANE_BUFS; ++q) widen((b + q) % LANE_BUFS);
+    return ok;
+  };
+  if (n && !on_lanes(nt, download)) return COUPE_ERR_CRASH;
+  if (timing)
+    fprintf(stderr, "coupe_b200 host path: %zu points, %u lanes: up %.1f ms, device %.1f ms, down %.1f ms\n", (size_t)n, nt,
+            ms_up, ms_run, ms_since(t_start) - ms_up - ms_run);
   return COUPE_ERR_OK;
+}
+
+// One process, several GPUs: the caller's arrays are sharded by contiguous index ranges
+// (SURVEY.md 8e), one host thread per GPU drives its context and the host threads are split between them.
+int run_host_group(coupe_b200_group *g, bool rib, uintptr_t *partition, uintptr_t dimension, uintptr_t n,
+                   const double *pts_host, int wtype, const void *w_host, const void *w_const,
+                   uintptr_t iter_count, double tolerance) {
+  if (!g || g->ctx.empty()) return COUPE_ERR_CRASH;
+  if (dimension != 2 && dimension != 3) return COUPE_ERR_BAD_DIMENSION;
+  if (wtype < 0 || wtype > 2) return COUPE_ERR_BAD_TYPE;
+  const unsigned world = (unsigned)g->ctx.size();
+  if (world == 1) return run_host(g->ctx[0], rib, partition, dimension, n, pts_host, wtype, w_host, w_const, iter_count, tolerance);
+  if (n == 0) return COUPE_ERR_OK;
+  if (!pts_host || !partition || (!w_host && !w_const)) return COUPE_ERR_CRASH;
+  const size_t wb = wtype == COUPE_INT ? 4 : 8;
+  const unsigned lanes = std::max(1u, host_threads() / world);
+  std::vector<int> errs(world, COUPE_ERR_OK);
+  auto rank_call = [&](unsigned r) {
+    const size_t base = n / world, rem = n % world;
+    const size_t b = r * base + std::min<size_t>(r, rem), e = b + base + (r < rem ? 1 : 0);
+    try {
+      errs[r] = run_host(g->ctx[r], rib, partition + b, dimension, e - b, pts_host + b * dimension, wtype,
+                         w_host ? static_cast<const char *>(w_host) + b * wb : nullptr, w_const, iter_count, tolerance,
+                         lanes);
+    } catch (const std::bad_alloc &) {
+      errs[r] = COUPE_ERR_ALLOC;
+    } catch (...) {
+      errs[r] = COUPE_ERR_CRASH;
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned r = 1; r < world; ++r) th.emplace_back(rank_call, r);
+  rank_call(0);
+  for (auto &t : th) t.join();
+  for (int e : errs)
+    if (e != COUPE_ERR_OK) return e;
+  return COUPE_ERR_OK;
+}
+
+// COUPE_B200_DEVICES=all | "0,1,2,3": coupe_rcb / coupe_rib use these GPUs of the box in one process.
+coupe_b200_group *g_group = nullptr;
+bool g_group_tried = false;
+coupe_b200_group *default_group() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (g_group_tried) return g_group;
+  g_group_tried = true;
+  const char *e = getenv("COUPE_B200_DEVICES");
+  if (!e || !*e) return nullptr;
+  std::vector<int> devs;
+  if (strcmp(e, "all") != 0) {
+    for (const char *p = e; *p;) {
+      char *end = nullptr;
+      const long v = strtol(p, &end, 10);
+      if (end == p) break;
+      devs.push_back((int)v);
+      p = *end == ',' ? end + 1 : end;
+    }
+    if (devs.empty()) return nullptr;
+  }
+  if (coupe_b200_group_create(&g_group, devs.empty() ? nullptr : devs.data(), (int)devs.size()) != COUPE_ERR_OK) {
+    fprintf(stderr, "coupe_b200: COUPE_B200_DEVICES=%s: cannot set up these devices\n", e);
+    g_group = nullptr;
+  }
+  return g_group;
 }
 
 coupe_err run(bool rib, uintptr_t *partition, uintptr_t dimension, const coupe_data *points,
@@ -224,10 +398,10 @@ coupe_err run(bool rib, uintptr_t *partition, uintptr_t dimension, const coupe_d
   if (dimension != 2 && dimension != 3) return COUPE_ERR_BAD_DIMENSION;  // lib.rs:297-301
   if (weights->type != COUPE_INT && weights->type != COUPE_INT64 && weights->type != COUPE_DOUBLE)
     return COUPE_ERR_BAD_TYPE;
-  std::lock_guard<std::mutex> lock(g_mu);
-  coupe_b200_ctx *ctx = default_ctx();
-  if (!ctx) return COUPE_ERR_CRASH;
   if (n == 0) return COUPE_ERR_OK;  // nothing to write (recursive_bisection.rs:685-688)
+  coupe_b200_group *group = getenv("COUPE_B200_DEVICES") ? default_group() : nullptr;
+  coupe_b200_ctx *ctx = group ? nullptr : default_ctx();
+  if (!group && !ctx) return COUPE_ERR_CRASH;  // no usable GPU: there is no CPU fallback
 
   // host views of the inputs
   std::vector<unsigned char> pts_tmp, w_tmp;
@@ -247,9 +421,27 @@ coupe_err run(bool rib, uintptr_t *partition, uintptr_t dimension, const coupe_d
     w_host = w_tmp.data();
   }
 
+  if (group)
+    return (coupe_err)run_host_group(group, rib, partition, dimension, n, static_cast<const double *>(pts_host),
+                                     (int)weights->type, w_host, w_const, iter_count, tolerance);
   return (coupe_err)run_host(ctx, rib, partition, dimension, n, static_cast<const double *>(pts_host),
                              (int)weights->type, w_host, w_const, iter_count, tolerance);
 }
+
+// ctx_destroy drops the per-context host state even when the caller forgot coupe_b200_host_release
+struct DestroyHook {
+  DestroyHook() {
+    cb_engine::on_destroy = [](coupe_b200_ctx *c) {
+      cudaSetDevice(cb_engine::device_of(c));
+      std::lock_guard<std::mutex> lock(g_mu);
+      auto it = g_host.find(c);
+      if (it != g_host.end()) {
+        free_lanes(it->second);
+        g_host.erase(it);
+      }
+    };
+  }
+} g_destroy_hook;
 
 coupe_data *make(coupe_data::Kind kind, uintptr_t len, coupe_type type, const void *ptr,
                  const void *(*i_th)(const void *, uintptr_t)) {
@@ -303,7 +495,6 @@ int coupe_b200_rcb_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim
                         uintptr_t iter_count, double tolerance) {
   if (!ctx) return COUPE_ERR_CRASH;
   try {
-    std::lock_guard<std::mutex> lock(g_mu);
     return run_host(ctx, false, partition, dim, n, points, wtype, weights, wconst, iter_count, tolerance);
   } catch (const std::bad_alloc &) {
     return COUPE_ERR_ALLOC;
@@ -317,7 +508,6 @@ int coupe_b200_rib_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim
                         uintptr_t iter_count, double tolerance) {
   if (!ctx) return COUPE_ERR_CRASH;
   try {
-    std::lock_guard<std::mutex> lock(g_mu);
     return run_host(ctx, true, partition, dim, n, points, wtype, weights, wconst, iter_count, tolerance);
   } catch (const std::bad_alloc &) {
     return COUPE_ERR_ALLOC;
@@ -326,13 +516,44 @@ int coupe_b200_rib_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim
   }
 }
 
+int coupe_b200_rcb_host_group(coupe_b200_group *group, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+                              const double *points, int wtype, const void *weights, const void *wconst,
+                              uintptr_t iter_count, double tolerance) {
+  try {
+    return run_host_group(group, false, partition, dim, n, points, wtype, weights, wconst, iter_count, tolerance);
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;
+  }
+}
+
+int coupe_b200_rib_host_group(coupe_b200_group *group, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+                              const double *points, int wtype, const void *weights, const void *wconst,
+                              uintptr_t iter_count, double tolerance) {
+  try {
+    return run_host_group(group, true, partition, dim, n, points, wtype, weights, wconst, iter_count, tolerance);
+  } catch (const std::bad_alloc &) {
+    return COUPE_ERR_ALLOC;
+  } catch (...) {
+    return COUPE_ERR_CRASH;
+  }
+}
+
 void coupe_b200_host_release(coupe_b200_ctx *ctx) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_staging.find(ctx);
-  if (it == g_staging.end()) return;
-  for (DevBuf *b : {&it->second.pts, &it->second.w, &it->second.part})
-    if (b->p) cudaFree(b->p);
-  g_staging.erase(it);
+  if (!ctx) return;
+  cb_engine::lock(ctx);
+  cudaSetDevice(cb_engine::device_of(ctx));
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_host.find(ctx);
+    if (it != g_host.end()) {
+      free_lanes(it->second);
+      g_host.erase(it);
+    }
+  }
+  cb_engine::release_host_buffers(ctx);
+  cb_engine::unlock(ctx);
 }
 
 enum coupe_err coupe_rcb(uintptr_t *partition, uintptr_t dimension, const coupe_data *points,

@@ -1785,11 +1785,14 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
 // ---------------------------------------------------------------------------
 // Final ids: last child choice, minus the smallest id present (:698-702).
 // ---------------------------------------------------------------------------
-template <class IDX>
+// OUT = unsigned long long: the caller's `usize` ids (out_vec: alignment of the caller's array);
+// OUT = uint16_t / uint32_t: the compact ids of the host path (engine-owned, aligned buffer), widened
+// to usize by the host threads that drain the device-to-host copy.
+template <class IDX, class OUT>
 __global__ void __launch_bounds__(512)
 emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp,
             const float4 *__restrict__ table, const float *__restrict__ table_split, int klast,
-            const GlobalParams *__restrict__ gp, unsigned long long *__restrict__ out, int out_vec,
+            const GlobalParams *__restrict__ gp, OUT *__restrict__ out, int out_vec,
             const uint32_t *guard) {
   pdl_wait();
   if (guard && *guard != 0) return;
@@ -1802,17 +1805,21 @@ emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp
     vv.load(idx, i0);
     uint32_t v[4];
     vv.get(v);
-    unsigned long long r[4] = {0, 0, 0, 0};
+    uint32_t r[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (i0 + j >= n) continue;
       const uint32_t p = v[j] >> klast;
       const uint32_t sbword = __float_as_uint(__ldg(&table[p]).w);
-      r[j] = (unsigned long long)(2 * p + child_of(v[j], sbword, xp, i0 + j, table_split + p) - off);
+      r[j] = 2 * p + child_of(v[j], sbword, xp, i0 + j, table_split + p) - off;
     }
-    if (i0 + 4 <= n && out_vec == 2) {  // 32-byte aligned output: one 256-bit streaming store per thread
-      asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + i0), "l"(r[0]), "l"(r[1]), "l"(r[2]),
-                   "l"(r[3])
+    if (sizeof(OUT) == 2) {  // the buffer is padded to a multiple of four ids
+      __stcs(reinterpret_cast<uint2 *>(out + i0), make_uint2(r[0] | (r[1] << 16), r[2] | (r[3] << 16)));
+    } else if (sizeof(OUT) == 4) {
+      __stcs(reinterpret_cast<uint4 *>(out + i0), make_uint4(r[0], r[1], r[2], r[3]));
+    } else if (i0 + 4 <= n && out_vec == 2) {  // 32-byte aligned output: one 256-bit streaming store per thread
+      asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + i0), "l"((unsigned long long)r[0]),
+                   "l"((unsigned long long)r[1]), "l"((unsigned long long)r[2]), "l"((unsigned long long)r[3])
                    : "memory");
     } else if (i0 + 4 <= n && out_vec) {
       __stcs(reinterpret_cast<ulonglong2 *>(out + i0), make_ulonglong2(r[0], r[1]));
@@ -1820,9 +1827,29 @@ emit_kernel(size_t n, const void *__restrict__ idx, const float *__restrict__ xp
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (i0 + j < n) out[i0 + j] = r[j];
+        if (i0 + j < n) out[i0 + j] = (OUT)r[j];
     }
   }
+}
+
+// Host path: the coordinate columns arrive narrowed from the host, so narrow_kernel does not run;
+// this samples the f64 weights the way it would (one run of 256 groups of four in 64).
+__global__ void __launch_bounds__(256)
+wsample_kernel(const double *__restrict__ wf64, size_t n, GlobalParams *gp, int w_sample) {
+  WStat ws;
+  ws.clear();
+  const size_t ngroups = (n + 3) / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // work items: every group, or with w_sample the 256 groups that open each run of 64 * 256
+  const size_t items = w_sample ? ((ngroups + 16383) / 16384) * 256 : ngroups;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += stride) {
+    const size_t g = w_sample ? (t >> 8) * 16384 + (t & 255) : t;
+    if (g >= ngroups) continue;
+    for (int j = 0; j < 4; ++j)
+      if (g * 4 + j < n) ws.add(__ldcs(wf64 + g * 4 + j));
+  }
+  ws.warp_reduce();
+  if ((threadIdx.x & 31) == 0) ws.commit(gp->wstat_sample);
 }
 
 // ---------------------------------------------------------------------------

@@ -86,9 +86,10 @@ int coupe_b200_rib_device(coupe_b200_ctx *ctx, void *stream, uint64_t *part_dev,
 		const void *wconst_host, uintptr_t iter_count, double tolerance);
 
 /*
- * The same two algorithms on HOST arrays with an explicit context: copies the
- * inputs to the device, runs the CUDA path, copies the n part ids back
- * (`partition` holds n uintptr_t, as in coupe_rcb).  This is what a language
+ * The same two algorithms on HOST arrays with an explicit context (`partition`
+ * holds n uintptr_t, as in coupe_rcb).  Host threads narrow the points to the f32
+ * columns the kernels read while they copy them up (RIB: the f64 points go up, the
+ * rotation precedes the narrowing) and widen the compact ids that come back.  This is what a language
  * binding that already holds plain slices calls (rust/coupe-gpu: `impl
  * Partition for GpuRcb`, replacing the body of coupe::Rcb::partition,
  * recursive_bisection.rs:805-811); coupe_rcb / coupe_rib of coupe.h are these
@@ -103,6 +104,28 @@ int coupe_b200_rib_host(coupe_b200_ctx *ctx, uintptr_t *partition, uintptr_t dim
 		const double *points, int wtype, const void *weights, const void *wconst,
 		uintptr_t iter_count, double tolerance);
 void coupe_b200_host_release(coupe_b200_ctx *ctx);
+
+/*
+ * One process, several GPUs of one box.  A group holds one context per device (`devices` lists
+ * `ndev` CUDA ordinals; ndev <= 0: every device of the box), ranks of an in-process NCCL
+ * communicator with the peer-memory exchange mapped by plain peer access.  The *_host_group calls
+ * shard the caller's HOST arrays by contiguous index ranges over the devices (one driving thread
+ * per GPU, the copy threads split between them) and write all n part ids: the same results as one
+ * GPU.  coupe_rcb / coupe_rib of coupe.h take this path when the environment variable
+ * COUPE_B200_DEVICES is set ("all", or a comma-separated list of ordinals).
+ */
+typedef struct coupe_b200_group coupe_b200_group;
+int coupe_b200_group_create(coupe_b200_group **out, const int *devices, int ndev);
+void coupe_b200_group_destroy(coupe_b200_group *group);
+int coupe_b200_group_size(const coupe_b200_group *group);
+/* Context of device i of the group (statistics, options); owned by the group. */
+coupe_b200_ctx *coupe_b200_group_ctx(coupe_b200_group *group, int i);
+int coupe_b200_rcb_host_group(coupe_b200_group *group, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+		const double *points, int wtype, const void *weights, const void *wconst,
+		uintptr_t iter_count, double tolerance);
+int coupe_b200_rib_host_group(coupe_b200_group *group, uintptr_t *partition, uintptr_t dim, uintptr_t n,
+		const double *points, int wtype, const void *weights, const void *wconst,
+		uintptr_t iter_count, double tolerance);
 
 /* Counters of the last call. */
 int coupe_b200_last_stats(const coupe_b200_ctx *ctx, coupe_b200_stats *out);

@@ -344,6 +344,51 @@ def test_edge_cases(cb, oracle):
     assert np.array_equal(part.cpu().numpy().astype(np.uint64), oracle.rcb(pts, w[1:].copy(), 7, 0.05))
 
 
+@pytest.mark.parametrize("dim,wk,iters,rib", [
+    (3, "f64", 10, False), (2, "i64", 12, False), (3, "i32", 9, False), (3, "const_f64", 8, False),
+    (2, "f64wide", 9, False), (3, "i64", 17, False),  # 17 levels: 4-byte compact ids on the way down
+    (3, "i64", 8, True), (2, "f64", 7, True),
+])
+def test_host_path_matches_device_path(cb, oracle, dim, wk, iters, rib):
+    """coupe_rcb / coupe_rib on host arrays (points narrowed by host threads into the engine's columns,
+    compact ids widened on the way out; RIB: f64 points uploaded) against the device entry point and the oracle;
+    several chunks per lane, a ragged last chunk."""
+    rng = np.random.default_rng(dim * 100 + iters)
+    n = 3 * (1 << 18) + 77
+    pts = gen_points(rng, n, dim, "cluster")
+    w = gen_weights(rng, n, wk)
+    dev_ids = run_device(cb, pts, w, iters, 0.05, rib=rib)
+    host_ids = run_host(cb, pts, w, iters, 0.05, rib=rib)
+    assert np.array_equal(host_ids, dev_ids)
+    if not rib:
+        assert np.array_equal(host_ids, oracle.rcb(pts, w, iters, 0.05, mode=1))
+    # an explicit context (the slice-level entry point of a language binding), pinned and pageable memory
+    ctx = cb.Context(0)
+    part = np.full(n, 2**63, dtype=np.uint64)
+    (cb.Rib if rib else cb.Rcb)(iters, 0.05, ctx).partition(part, (pts, w))
+    assert np.array_equal(part, dev_ids)
+    tp = torch.from_numpy(pts).pin_memory()
+    tw = torch.from_numpy(w).pin_memory() if w.ndim else None
+    tpart = torch.zeros(n, dtype=torch.int64).pin_memory()
+    (cb.Rib if rib else cb.Rcb)(iters, 0.05, ctx).partition(tpart.numpy().view(np.uint64),
+                                                          (tp.numpy(), tw.numpy() if tw is not None else w))
+    assert np.array_equal(tpart.numpy().view(np.uint64), dev_ids)
+    ctx.close()
+
+
+def test_host_path_small_and_odd_inputs(cb, oracle):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 5, 1000, (1 << 18) - 1, (1 << 18) + 1):
+        pts = rng.normal(size=(n, 3))
+        w = rng.integers(1, 9, n).astype(np.int64)
+        assert np.array_equal(run_host(cb, pts, w, 4, 0.05), oracle.rcb(pts, w, 4, 0.05))
+    pts = rng.normal(size=(1000, 2))
+    assert run_host(cb, pts, np.ones(1000), 0, 0.05).tolist() == [0] * 1000  # iter_count 0
+    # NaN / infinite coordinates must not crash the host narrowing (results then follow f32 comparisons)
+    pts[5, 0] = np.inf
+    run_host(cb, pts, np.ones(1000), 3, 0.05)
+
+
 def test_iter_count_limits(cb, oracle):
     """Up to 2^24 parts (most of them empty here); beyond that COUPE_ERR_ALLOC, not a crash (include/coupe.h)."""
     rng = np.random.default_rng(8)

@@ -146,3 +146,63 @@ def test_sharded_rib_matches_single_gpu(two_gpus):
     # the moment sums are f64 and depend on the shard boundaries in the last bits: ids may differ
     # only for points within rounding of a cut plane
     assert (got != one).mean() < 1e-4
+
+
+@pytest.mark.parametrize("wkind,dim,iters,rib", [("f64", 3, 10, False), ("i64", 2, 12, False), ("f64lognormal", 3, 8, False),
+                                               ("const", 3, 9, False), ("i64", 3, 7, True)])
+def test_in_process_group_on_host_arrays(two_gpus, oracle, wkind, dim, iters, rib):
+    """One process, every GPU of the box (coupe_b200_group_create + the *_host_group calls): the caller's host
+    arrays are sharded over the devices; same ids as one GPU and as the oracle."""
+    import coupe_b200
+
+    rng = np.random.default_rng(21)
+    n = 1_200_007
+    pts = rng.normal(size=(n, dim)) * np.array([5.0, 1.0, 0.3])[:dim]
+    w = {"i64": rng.integers(1, 100, n).astype(np.int64), "f64": rng.uniform(0.5, 1.5, n),
+         "f64lognormal": rng.lognormal(0.0, 5.0, n), "const": np.array(2.5)}[wkind]
+    group = coupe_b200.Group()  # all devices
+    assert group.size == torch.cuda.device_count()
+    algo = (coupe_b200.Rib if rib else coupe_b200.Rcb)(iters, 0.05, group)
+    part = np.full(n, 2**63, dtype=np.uint64)
+    algo.partition(part, (pts, w))
+    again = np.zeros(n, dtype=np.uint64)
+    algo.partition(again, (pts, w))
+    assert np.array_equal(part, again)
+    st = group.contexts[0].stats()
+    assert st["n_global"] == n and st["peer_exchange"] == 1
+    one = np.zeros(n, dtype=np.uint64)
+    (coupe_b200.Rib if rib else coupe_b200.Rcb)(iters, 0.05).partition(one, (pts, w))
+    if rib:  # the moment sums depend on the shard boundaries in the last bits
+        assert (part != one).mean() < 1e-4
+    else:
+        assert np.array_equal(part, one)
+        assert np.array_equal(part, oracle.rcb(pts, w, iters, 0.05, mode=1))
+    group.close()
+
+
+def test_coupe_rcb_uses_the_box_when_asked(two_gpus, oracle, tmp_path):
+    """The reference-compatible entry point itself: a C-level caller (here a fresh process through ctypes) sets
+    COUPE_B200_DEVICES=all and plain coupe_rcb shards its host arrays over every GPU."""
+    import subprocess
+    import sys
+
+    rng = np.random.default_rng(5)
+    n = 900_001
+    pts = rng.random((n, 3))
+    w = rng.integers(1, 50, n).astype(np.int64)
+    np.save(tmp_path / "pts.npy", pts)
+    np.save(tmp_path / "w.npy", w)
+    code = f"""
+import numpy as np, sys
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import coupe_b200
+pts, w = np.load({str(tmp_path / 'pts.npy')!r}), np.load({str(tmp_path / 'w.npy')!r})
+part = np.zeros(len(pts), dtype=np.uint64)
+coupe_b200.Rcb(9, 0.05).partition(part, (pts, w))   # -> coupe_rcb of include/coupe.h
+np.save({str(tmp_path / 'part.npy')!r}, part)
+"""
+    env = dict(os.environ, COUPE_B200_DEVICES="all", NCCL_DEBUG="WARN", COUPE_B200_HOST_TIMING="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stderr.count("coupe_b200 host path:") == torch.cuda.device_count()  # one shard per GPU
+    assert np.array_equal(np.load(tmp_path / "part.npy"), oracle.rcb(pts, w, 9, 0.05))
