@@ -589,6 +589,7 @@ def run_ours(args):
     sweeps = []  # (ms, level, kind) of the timed steps
     refine_n = 0
     refine_pts = 0
+    xwait = 0.0
     stats_last = None
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -606,6 +607,7 @@ def run_ours(args):
             sweeps += ctx.sweep_times()
         refine_n += st["refine_sweeps"]
         refine_pts += st["refine_points"]
+        xwait += st["exchange_wait_ms"]
         stats_last = st
     e1.record()
     barrier()
@@ -759,6 +761,7 @@ def run_ours(args):
                 "f64_weight_form": None if cfg["weights"] not in ("f64", "linear") else ("wide" if wide else "narrow"),
                 "peer_exchange": int(stats_last["peer_exchange"]) if stats_last else None,
                 "collectives_per_step": int(stats_last["collectives"]) if stats_last else None,
+                "exchange_wait_ms_per_step_rank0": round(xwait / args.steps, 4),
                 "host_syncs_per_step": int(stats_last["host_syncs"]) if stats_last else None},
         "parity": parity,
         "clocks": clocks,

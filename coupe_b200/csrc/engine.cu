@@ -216,6 +216,7 @@ bool inverse(int D, const double *a, double *o) {  // cofactor inverse (try_inve
 struct coupe_b200_ctx {
   int device = 0;
   int num_sms = 148;
+  int sm_khz = 0;  // SM clock (kHz): converts clock64() differences to time
   size_t max_smem = 0;
   std::mutex mu;
   // scratch
@@ -238,6 +239,9 @@ struct coupe_b200_ctx {
   unsigned int *xchg_aux = nullptr;                       // {ticket, error}
   // options
   int kmax_a = 8, nb_smem_log2 = 14, kmax_refine = 10, force_global = 0, trace_on = 1, time_sweeps = 0;
+  int smem_pad = 0;      // experiments: bytes added to the dense sweeps' dynamic shared memory request
+  int table_rep_max = 3; // experiments: cap on the bank-private copies of the per-parent table (log2)
+  int carve_fit = 1;     // keep the dense sweeps under the 196 KB shared-memory carve-out when the tables allow it
   int sample_w_opt = 1;  // f64 weights: max |w| from a sample, verified by the root sweep
   std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
   std::vector<int> event_kind;      // 0 dense, 1 refine
@@ -256,11 +260,18 @@ void setup_xchg(coupe_b200_ctx *c);
 // Shared memory of a dense sweep in shared-memory mode: the three histogram arrays at fixed
 // offsets (rcb_kernels.cuh: HIST_BYTES), then the per-parent table replicated 2^rep_log2 times,
 // the split positions and the bracket ends.
-size_t sweep_smem_bytes(int level, int rep_log2) {
+size_t sweep_smem_bytes(int level, int rep_log2, bool aux) {
   const size_t parents = (size_t)1 << (level > 0 ? level - 1 : 0);
-  return HIST_BYTES + (parents << rep_log2) * sizeof(float4) + parents * 2 * sizeof(float) +
-         ((((size_t)2 << level) + 15) & ~(size_t)15);  // + the per-node shifts (f64 weights, wide form)
+  size_t b = HIST_BYTES + (parents << rep_log2) * sizeof(float4);
+  // the rarely read values: split positions, bracket ends, per-node shifts (f64 weights, wide form)
+  if (aux) b += parents * 2 * sizeof(float) + ((((size_t)2 << level) + 15) & ~(size_t)15);
+  return b;
 }
+// Shared memory is carved out of the SM's 228 KB in steps (..., 164, 196, 228 KB, 1 KB of each reserved by the
+// system); what is left is the L1 cache and the staging of global loads.  A sweep that needs a few bytes more
+// than 195 KB gets the 228 KB carve-out and no L1 at all, and runs 20 % slower (levels 6-9 of round 1): the
+// tables are therefore shrunk (fewer bank-private copies, rare values read from global memory) to stay below.
+constexpr size_t SMEM_CARVE_196 = 196 * 1024 - 1024;
 
 template <int WIN, bool ROOT>
 void launch_sweep(bool smem, bool tsm, bool idx16, int grid, size_t bytes, cudaStream_t st,
@@ -334,6 +345,7 @@ struct FirstPlan {
   bool smem;           // block-private shared-memory histograms, else L2 atomics
   int copies_log2;     // privatised copies per block (smem mode)
   bool table_in_smem;  // per-parent table staged in shared memory
+  bool aux_in_smem;    // ... and the rarely read per-parent values with it
   int table_rep_log2;  // ... replicated 2^this times (bank-private copies at the deep levels)
   size_t bytes;        // dynamic shared memory
 };
@@ -345,9 +357,24 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
   p.table_in_smem = true;
   if (p.smem) {
     p.copies_log2 = std::min(5, c->nb_smem_log2 - (level + p.k));
-    p.table_rep_log2 = 3;
-    while (p.table_rep_log2 > 0 && sweep_smem_bytes(level, p.table_rep_log2) > c->max_smem) --p.table_rep_log2;
-    p.bytes = sweep_smem_bytes(level, p.table_rep_log2);
+    // first choice: under the 196 KB carve-out (L1 kept), with as many table copies as fit, the rare values
+    // staged if there is room for them; else the whole 227 KB
+    p.table_rep_log2 = -1;
+    if (c->carve_fit)
+      for (int aux = 1; aux >= 0 && p.table_rep_log2 < 0; --aux)
+        for (int rep = c->table_rep_max; rep >= 0; --rep)
+          if (sweep_smem_bytes(level, rep, aux != 0) <= SMEM_CARVE_196) {
+            p.table_rep_log2 = rep;
+            p.aux_in_smem = aux != 0;
+            break;
+          }
+    if (p.table_rep_log2 < 0) {
+      p.aux_in_smem = true;
+      p.table_rep_log2 = c->table_rep_max;
+      while (p.table_rep_log2 > 0 && sweep_smem_bytes(level, p.table_rep_log2, true) > c->max_smem) --p.table_rep_log2;
+    }
+    p.bytes = sweep_smem_bytes(level, p.table_rep_log2, p.aux_in_smem);
+    if (p.bytes + c->smem_pad <= c->max_smem) p.bytes += c->smem_pad;
     if (p.bytes > c->max_smem) p.smem = false;
   }
   if (!p.smem) {
@@ -357,6 +384,7 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
     const size_t tb = ((size_t)1 << (level > 0 ? level - 1 : 0)) * (sizeof(float4) + 2 * sizeof(float)) +
                       ((((size_t)2 << level) + 15) & ~(size_t)15);
     p.table_in_smem = tb <= 64 * 1024;
+    p.aux_in_smem = p.table_in_smem;
     p.bytes = p.table_in_smem ? tb : 0;
   }
   return p;
@@ -657,7 +685,8 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     rt_bytes = ((size_t)1 << level) * sizeof(uint32_t);
     rts = rt_bytes <= 64 * 1024;
     const size_t fixed = (size_t)REFINE_QBYTES + (rts ? rt_bytes : 0) + 64;
-    return (uint32_t)std::min<size_t>((size_t)1 << c->nb_smem_log2, (c->max_smem - fixed) / 12);
+    const size_t room = c->carve_fit ? SMEM_CARVE_196 : c->max_smem;  // stay under the 196 KB carve-out (see SMEM_CARVE_196)
+    return (uint32_t)std::min<size_t>((size_t)1 << c->nb_smem_log2, (room - fixed) / 12);
   };
   // ---- level loop -----------------------------------------------------------------
   // No stream synchronisation inside: the rank kernel that ends every pass writes the
@@ -745,6 +774,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.w_vec = ((uintptr_t)wp % 16) == 0;
     sa.one = 1;
     sa.table_rep_log2 = plan.table_rep_log2;
+    sa.aux_in_smem = plan.aux_in_smem ? 1 : 0;
     if (!plan.smem) {
       launch_pdl(fill_hist_kernel, (nb + 255) / 256, 256, 0, st, hist_w, hist_min, nb, guard);
       R.launched();
@@ -896,6 +926,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   CU(cudaMemcpyAsync(c->h_pinned + 2, &gp->refine_points, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned + 6, &gp->ec, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_pinned + 8, &gp->xchg_wait_cycles, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned + 5, &gp->nocarry, 4, cudaMemcpyDeviceToHost, st));
   if (use_xchg) CU(cudaMemcpyAsync(c->h_pinned + 1, c->xchg_aux + 1, 4, cudaMemcpyDeviceToHost, st));
   R.sync();
@@ -905,6 +936,9 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     memcpy(&ec, c->h_pinned + 6, 4);
     S.weight_shift = wtype == WT_F64 ? sh - ec : 0;
     S.weight_wide = f64_wide;
+    unsigned long long cyc;
+    memcpy(&cyc, c->h_pinned + 8, 8);
+    S.exchange_wait_ms = c->sm_khz > 0 ? (double)cyc / (double)c->sm_khz : 0.0;
   }
   S.peer_exchange = use_xchg ? 1 : 0;
   S.carry_free = c->h_pinned[5];
@@ -1102,6 +1136,7 @@ int coupe_b200_ctx_create(coupe_b200_ctx **out, int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     c->max_smem = prop.sharedMemPerBlockOptin;
+    CU(cudaDeviceGetAttribute(&c->sm_khz, cudaDevAttrClockRate, device));
     CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_pinned), 64 * sizeof(uint32_t) * 4,
                      cudaHostAllocDefault));
     void *hf = nullptr;
@@ -1352,6 +1387,9 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "time_sweeps") c->time_sweeps = (int)value;
   else if (s == "peer_exchange") c->use_xchg_opt = value != 0;
   else if (s == "sample_weights") c->sample_w_opt = value != 0;
+  else if (s == "carve_fit") c->carve_fit = value != 0;
+  else if (s == "smem_pad") c->smem_pad = (int)std::max<int64_t>(0, std::min<int64_t>(32768, value));
+  else if (s == "table_rep_max") c->table_rep_max = (int)std::max<int64_t>(0, std::min<int64_t>(3, value));
   else return COUPE_ERR_NOT_FOUND;
   return COUPE_ERR_OK;
 }

@@ -51,6 +51,8 @@ coupe_b200_ctx *default_ctx() {
 
 size_t type_size(coupe_type t) { return t == COUPE_INT ? 4 : 8; }
 
+// Host threads of one call: COUPE_B200_HOST_THREADS, else the cores this process may run on, shared
+// with the other ranks of a one-process-per-GPU launch on the same box (LOCAL_WORLD_SIZE, as torchrun sets it).
 unsigned host_threads() {
   static const unsigned n = [] {
     if (const char *e = getenv("COUPE_B200_HOST_THREADS"))
@@ -59,10 +61,16 @@ unsigned host_threads() {
     unsigned c = 0;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) c = (unsigned)CPU_COUNT(&set);
     if (c == 0) c = std::thread::hardware_concurrency();
+    if (const char *e = getenv("LOCAL_WORLD_SIZE"))
+      if (atoi(e) > 1) c = std::max(1u, c / (unsigned)atoi(e));
     return std::max(1u, std::min(c, 32u));
   }();
   return n;
 }
+// Below this many host threads per GPU, points in memory the caller has pinned go up as they are (the DMA
+// engines need no host work; narrow_kernel narrows them on the device): 8 B per coordinate over PCIe instead
+// of 4, but a few threads narrow more slowly than the link moves the wider data.
+constexpr unsigned NARROW_ON_HOST_MIN_LANES = 8;
 
 // Materialise a Constant or Fn data set into `out` (elem bytes per element);
 // Fn callbacks are evaluated from several threads, as the reference does with rayon.
@@ -209,16 +217,20 @@ int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dime
   if (cudaSetDevice(device) != cudaSuccess) return COUPE_ERR_CRASH;
   const int D = (int)dimension;
   const size_t wb = w_host ? (wtype == COUPE_INT ? 4 : 8) : 0;
+  if (lane_budget == 0) lane_budget = host_threads();
+  static const int force_raw = [] { const char *e = getenv("COUPE_B200_HOST_NARROW"); return e && *e ? (*e == '0' ? 1 : -1) : 0; }();
+  // raw: the f64 points themselves go up (RIB always: the rotation precedes the narrowing)
+  const bool raw = rib || force_raw > 0 ||
+                   (force_raw == 0 && n && lane_budget < NARROW_ON_HOST_MIN_LANES && is_pinned(pts_host));
   HostColumns cols{};
-  int err = cb_engine::host_columns(ctx, n, dimension, wb, rib, iter_count, &cols);
+  int err = cb_engine::host_columns(ctx, n, dimension, wb, raw, iter_count, &cols);
   if (err != COUPE_ERR_OK) return err;
   const size_t nchunks = (n + CHUNK_POINTS - 1) / CHUNK_POINTS;
-  if (lane_budget == 0) lane_budget = host_threads();
   const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(lane_budget, nchunks));
   HostState *hs = host_state(ctx, lane_budget);
   if (!hs) return COUPE_ERR_ALLOC;
   const bool w_pinned = w_host && is_pinned(w_host);
-  const bool p_pinned = rib && n && is_pinned(pts_host);
+  const bool p_pinned = raw && n && is_pinned(pts_host);
 
   static const bool timing = [] { const char *e = getenv("COUPE_B200_HOST_TIMING"); return e && *e && *e != '0'; }();
   const auto t_start = std::chrono::steady_clock::now();
@@ -240,14 +252,14 @@ int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dime
       if (pending[b]) ok = cudaEventSynchronize(l.done[b]) == cudaSuccess;  // the buffer's previous copy is over
       char *buf = static_cast<char *>(l.buf[b]);
       size_t used = 0;
-      if (!rib) {
+      if (!raw) {
         float *s = reinterpret_cast<float *>(buf);
         if (D == 2) cb_host::narrow_chunk<2>(pts_host, lo, hi, s, m, &bmin[t * 3], &bmax[t * 3]);
         else cb_host::narrow_chunk<3>(pts_host, lo, hi, s, m, &bmin[t * 3], &bmax[t * 3]);
         for (int d = 0; d < D && ok; ++d)
           ok = cudaMemcpyAsync(cols.x[d] + lo, s + (size_t)d * m, m * 4, cudaMemcpyHostToDevice, l.stream) == cudaSuccess;
         used = (size_t)D * m * 4;
-      } else {  // RIB: the f64 points themselves
+      } else {  // the f64 points themselves
         const size_t bytes = m * D * 8;
         const char *src = reinterpret_cast<const char *>(pts_host + lo * D);
         if (!p_pinned) {
@@ -287,7 +299,7 @@ int run_host(coupe_b200_ctx *ctx, bool rib, uintptr_t *partition, uintptr_t dime
   const double ms_up = ms_since(t_start);
   // ---- the CUDA path --------------------------------------------------------------------------------
   int id_bytes = 0;
-  err = cb_engine::run_locked(ctx, rib, nullptr, rib ? nullptr : &pre, &id_bytes, dimension, n, cols.pts_raw, wtype,
+  err = cb_engine::run_locked(ctx, rib, nullptr, raw ? nullptr : &pre, &id_bytes, dimension, n, cols.pts_raw, wtype,
                               w_host ? cols.w : nullptr, w_const, iter_count, tolerance);
   if (err != COUPE_ERR_OK) return err;
 

@@ -77,6 +77,7 @@ struct GlobalParams {
   uint32_t w_negative;             // ... whether any is negative
   uint32_t nocarry;                // decided after the root pass: 32-bit block-private sums cannot overflow
   unsigned long long refine_points;  // points the refinement sweeps of the call re-binned (statistics)
+  unsigned long long xchg_wait_cycles;  // multi-GPU: SM cycles block 0 of the walks spent waiting for the other ranks' histograms
   int shift;                       // f64 weights: shift of the root pass, normalised weights (value of a unit: 2^(ec - shift))
 };
 
@@ -483,6 +484,7 @@ struct SweepArgs {
   int copies_log2;           // SMEM mode: 2^copies_log2 lane-private copies per block
   int w_vec;                 // weights are 16-byte aligned
   int table_rep_log2;        // the staged per-parent table is replicated 2^this times (bank-private copies)
+  int aux_in_smem;           // the rarely read per-parent / per-node values (split position, bracket end, f64 shift) are staged too
   uint32_t one;              // 1, from the host: a literal 1 turns `red.shared.add` into ATOMS.POPC.INC,
                              // which is several times slower than ATOMS.ADD on scattered addresses
 };
@@ -745,9 +747,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   // reads copy l % 2^rlog: with 8 copies every lane of a quarter warp owns its bank group.
   const int rlog = TSM ? a.table_rep_log2 : 0;
   const uint32_t rep_lane = threadIdx.x & ((1u << rlog) - 1);
+  const bool aux = TSM && a.aux_in_smem != 0;
   float *s_split = reinterpret_cast<float *>(s_table + (TSM ? ((size_t)nparents << rlog) : 0));
-  float *s_thi = s_split + (TSM ? nparents : 0);
-  short *s_nshift = reinterpret_cast<short *>(s_thi + (TSM ? nparents : 0));  // [nodes of this level], wide f64 only
+  float *s_thi = s_split + (aux ? nparents : 0);
+  short *s_nshift = reinterpret_cast<short *>(s_thi + (aux ? nparents : 0));  // [nodes of this level], wide f64 only
   constexpr bool WIDE_LEVEL = !ROOT && WIN == WIN_F64;  // below the root f64 weights are read only in the wide form
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i + 1 <= nwords; i += blockDim.x) {  // (i < nwords; written so for nwords == 0)
@@ -761,11 +764,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   if (a.guard && *a.guard != 0) return;
   if (TSM) {
     for (int i = threadIdx.x; i < (nparents << rlog); i += blockDim.x) s_table[i] = a.table[i >> rlog];
-    for (int i = threadIdx.x; i < nparents; i += blockDim.x) {
+    for (int i = threadIdx.x; aux && i < nparents; i += blockDim.x) {
       s_split[i] = a.table_split[i];
       s_thi[i] = a.table_hi[i];
     }
-    if (WIDE_LEVEL)
+    if (WIDE_LEVEL && aux)
       for (int i = threadIdx.x; i < (1 << level); i += blockDim.x) s_nshift[i] = a.nshift[i];
   }
   __syncthreads();
@@ -827,7 +830,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
         const uint32_t p = pv[j] >> kprev;
         const uint32_t tw = __float_as_uint(TSM ? s_table[(p << rlog) + rep_lane].w : __ldg(&a.table[p]).w);
         if (2 * pv[j] + 1 == tw) {
-          const float split = TSM ? s_split[p] : __ldg(a.table_split + p);
+          const float split = aux ? s_split[p] : __ldg(a.table_split + p);
           sel[j] = !(__ldg(a.xp + i0 + j) < split) ? sel_right : sel_left;
         }
       }
@@ -841,7 +844,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
         const float tf = __fadd_rd(t, 8388608.f);
         const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
         if (!(fabsf(fr - 0.5f) < e.z))
-          slot[j] = 0x4B000000u + descend_exact(x[j], e.x, TSM ? s_thi[p] : __ldg(a.table_hi + p), k);
+          slot[j] = 0x4B000000u + descend_exact(x[j], e.x, aux ? s_thi[p] : __ldg(a.table_hi + p), k);
       }
     }
 #pragma unroll
@@ -859,7 +862,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
           ws.add(r[j]);
         } else {  // the node's own shift
           const uint32_t node = slot[j] >> k;
-          const int sh = TSM ? s_nshift[node] : __ldg(a.nshift + node);
+          const int sh = aux ? s_nshift[node] : __ldg(a.nshift + node);
           w[j] = quantise_f64(r[j], norm, pow2_f64(sh), true);
         }
       }
@@ -1165,8 +1168,10 @@ template <>
 struct IdxVec<uint16_t> {
   static constexpr int N = 8;
   uint4 v;
+  // default cache policy, not a streaming load: the drain gathers idx[i] of the matched points again a few
+  // microseconds later and should find the line in L2 (a streaming load is evicted first: 2 % L2 hits)
   __device__ __forceinline__ void load(const void *p, size_t g) {
-    v = __ldcs(reinterpret_cast<const uint4 *>(p) + g);
+    v = __ldg(reinterpret_cast<const uint4 *>(p) + g);
   }
   __device__ __forceinline__ void get(uint32_t (&o)[8]) const {
     o[0] = v.x & 0xFFFFu; o[1] = v.x >> 16; o[2] = v.y & 0xFFFFu; o[3] = v.y >> 16;
@@ -1178,7 +1183,7 @@ struct IdxVec<uint32_t> {
   static constexpr int N = 4;
   uint4 v;
   __device__ __forceinline__ void load(const void *p, size_t g) {
-    v = __ldcs(reinterpret_cast<const uint4 *>(p) + g);
+    v = __ldg(reinterpret_cast<const uint4 *>(p) + g);
   }
   __device__ __forceinline__ void get(uint32_t (&o)[4]) const { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 };
@@ -1511,6 +1516,7 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
           }
         }
       }
+      if (blockIdx.x == 0) a.gp->xchg_wait_cycles += (unsigned long long)(clock64() - t0);
       __threadfence();
     }
     __syncthreads();

@@ -537,6 +537,16 @@ int coupe_b200_mewe_write(const char *path, int is_integer, uint16_t criterion_c
   return ok ? COUPE_ERR_OK : COUPE_ERR_CRASH;
 }
 
+// Bytes left in the file from the current position (-1 if unknown): counts read from a file are
+// checked against it before anything is allocated, so a corrupt header cannot ask for 2^64 bytes.
+static long long bytes_left(FILE *f) {
+  const long at = ftell(f);
+  if (at < 0 || fseek(f, 0, SEEK_END) != 0) return -1;
+  const long end = ftell(f);
+  if (end < 0 || fseek(f, at, SEEK_SET) != 0) return -1;
+  return (long long)end - at;
+}
+
 int coupe_b200_mewe_read(const char *path, int *is_integer, uint16_t *criterion_count, uint64_t *count,
                          void **values) {
   if (!path || !is_integer || !criterion_count || !count || !values) return COUPE_ERR_CRASH;
@@ -558,6 +568,8 @@ int coupe_b200_mewe_read(const char *path, int *is_integer, uint16_t *criterion_
     if (*criterion_count != 0) {  // weight.rs:97-99: zero criteria reads as an empty integer array
       uint64_t n = 0;
       if (!get(f, &n, 8)) rc = COUPE_ERR_CRASH;
+      else if (const long long left = bytes_left(f);
+               left < 0 || n > (uint64_t)left / 8 / *criterion_count) rc = COUPE_ERR_CRASH;  // truncated or corrupt
       else {
         const size_t bytes = (size_t)n * *criterion_count * 8;
         void *buf = malloc(bytes ? bytes : 1);
@@ -599,6 +611,7 @@ int coupe_b200_mepe_read(const char *path, uint64_t *count, uint64_t **ids) {
   if (!get(f, magic, 4)) rc = COUPE_ERR_CRASH;
   else if (memcmp(magic, "MePe", 4) != 0) rc = COUPE_ERR_BAD_TYPE;
   else if (!get(f, &n, 8)) rc = COUPE_ERR_CRASH;
+  else if (const long long left = bytes_left(f); left < 0 || n > (uint64_t)left / 8) rc = COUPE_ERR_CRASH;  // truncated or corrupt
   else {
     uint64_t *buf = static_cast<uint64_t *>(malloc(n ? (size_t)n * 8 : 1));
     if (!buf) rc = COUPE_ERR_ALLOC;

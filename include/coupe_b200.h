@@ -52,6 +52,8 @@ typedef struct coupe_b200_stats {
 	double   dense_sweep_ms; /* option "time_sweeps": summed device time of the dense sweeps */
 	double   refine_sweep_ms;/* option "time_sweeps": summed device time of the refinement sweeps */
 	uint64_t refine_points;  /* points re-binned by the refinement sweeps (this rank) */
+	double   exchange_wait_ms; /* multi-GPU, peer-memory exchange: time the walks of this rank waited for the other
+	                              ranks' histograms (first block of every pass, SM cycles at the nominal clock) */
 } coupe_b200_stats;
 
 /* One context per process and GPU.  `device` is a CUDA ordinal.  Returns a

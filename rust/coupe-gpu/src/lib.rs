@@ -35,6 +35,7 @@ pub enum WType {
 extern "C" {
     fn coupe_b200_ctx_create(out: *mut *mut Ctx, device: c_int) -> c_int;
     fn coupe_b200_ctx_destroy(ctx: *mut Ctx);
+    fn coupe_b200_host_release(ctx: *mut Ctx);
     fn coupe_b200_rcb_host(
         ctx: *mut Ctx, partition: *mut usize, dim: usize, n: usize, points: *const f64,
         wtype: c_int, weights: *const c_void, wconst: *const c_void, iter_count: usize,
@@ -94,7 +95,11 @@ impl Context {
 }
 impl Drop for Context {
     fn drop(&mut self) {
-        unsafe { coupe_b200_ctx_destroy(self.0) }
+        // the device and pinned buffers of the *_host entry points, then the context itself
+        unsafe {
+            coupe_b200_host_release(self.0);
+            coupe_b200_ctx_destroy(self.0)
+        }
     }
 }
 

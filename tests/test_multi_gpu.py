@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def _worker(rank, world, port, case, out):
+def _worker(rank, world, port, cases, out):
     import torch.distributed as dist
 
     import coupe_b200
@@ -22,33 +22,37 @@ def _worker(rank, world, port, case, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        pts, w, iters, tol, rib, empty_last, peer = case
-        n = pts.shape[0]
-        b, e = cdist.shard_range(n, rank, world)
-        if rank == world - 1 and empty_last:  # last rank holds nothing
-            b = e = n
-        elif empty_last:
-            b, e = cdist.shard_range(n, rank, world - 1)
         ctx = cdist.init_comm(coupe_b200.Context(rank))
-        ctx.set_option("peer_exchange", int(peer))
-        part = torch.full((e - b,), -1, dtype=torch.int64, device=dev)
-        tw = torch.from_numpy(w[b:e]).to(dev) if w.ndim else w
-        algo = (coupe_b200.Rib if rib else coupe_b200.Rcb)(iters, tol, ctx)
-        algo.partition(part, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
-        torch.cuda.synchronize()
-        calls = 3  # several calls on one context: the exchange slots and flags are reused across calls
-        for _ in range(calls - 1):
-            again = torch.full_like(part, -1)
-            algo.partition(again, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
-            assert torch.equal(again, part)
-        st = ctx.stats()
-        out.put((rank, b, part.cpu().numpy().astype(np.uint64), st["collectives"], st["peer_exchange"]))
+        results = []
+        for pts, w, iters, tol, rib, empty_last, peer in cases:
+            n = pts.shape[0]
+            b, e = cdist.shard_range(n, rank, world)
+            if rank == world - 1 and empty_last:  # last rank holds nothing
+                b = e = n
+            elif empty_last:
+                b, e = cdist.shard_range(n, rank, world - 1)
+            ctx.set_option("peer_exchange", int(peer))
+            part = torch.full((e - b,), -1, dtype=torch.int64, device=dev)
+            tw = torch.from_numpy(w[b:e]).to(dev) if w.ndim else w
+            algo = (coupe_b200.Rib if rib else coupe_b200.Rcb)(iters, tol, ctx)
+            algo.partition(part, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
+            torch.cuda.synchronize()
+            calls = 3  # several calls on one context: the exchange slots and flags are reused across calls
+            for _ in range(calls - 1):
+                again = torch.full_like(part, -1)
+                algo.partition(again, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
+                assert torch.equal(again, part)
+            st = ctx.stats()
+            results.append((part.cpu().numpy().astype(np.uint64), st["peer_exchange"], st["n_global"]))
+        out.put((rank, results))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def run_sharded(case, world=2):
+def run_sharded(cases, world=2):
+    """Runs every case (pts, w, iters, tol, rib, empty_last, peer) in ONE process group of `world` ranks (a
+    rendezvous and an NCCL set-up cost ten seconds) and returns the concatenated ids of each."""
     import torch.multiprocessing as mp
 
     s = socket.socket()
@@ -57,22 +61,18 @@ def run_sharded(case, world=2):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=300) for _ in procs), key=lambda t: (t[0]))
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
-    assert all(r[3] > 0 for r in res), "no NCCL collective was issued"
-    peer = case[-1]
-    assert all(r[4] == int(peer) for r in res), "peer-memory exchange was requested but not used (or the reverse)"
-    return np.concatenate([r[2] for r in res])
-
-
-@pytest.fixture(scope="module")
-def two_gpus():
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs two CUDA devices")
+    out = []
+    for i, case in enumerate(cases):
+        assert all(r[1][i][1] == int(case[-1]) for r in res), "peer-memory exchange was requested but not used (or the reverse)"
+        assert all(r[1][i][2] == case[0].shape[0] for r in res)
+        out.append(np.concatenate([r[1][i][0] for r in res]))
+    return out
 
 
 def _world_or_skip(world):
@@ -80,53 +80,54 @@ def _world_or_skip(world):
         pytest.skip(f"needs {world} CUDA devices")
 
 
-@pytest.mark.parametrize("peer", [True, False], ids=["peer-exchange", "nccl"])
-@pytest.mark.parametrize("wkind,dim,iters,tol,empty_last", [
+@pytest.fixture(scope="module")
+def two_gpus():
+    _world_or_skip(2)
+
+
+# wkind, dim, iters, tol, empty_last
+RCB_CASES = [
     ("i64", 3, 10, 0.05, False),
     ("f64", 3, 9, 0.05, False),
     ("i64big", 2, 8, 0.001, False),
     ("const", 2, 7, 0.0, True),
-    ("f64outlier", 3, 8, 0.05, False),  # one huge weight on the second rank, outside every sampled run
-    ("i64", 2, 6, 0.05, True),          # array weights and an empty last shard: same collective steps on every rank
+    ("f64outlier", 3, 8, 0.05, False),   # one huge weight on the last rank, outside every sampled run: wide form
+    ("i64", 2, 6, 0.05, True),           # array weights and an empty last shard: same collective steps on every rank
     ("f64", 3, 6, 0.05, True),
     ("f64lognormal", 3, 8, 0.02, False),  # wide form: per-node units, f64 weights re-read at every level
     ("f64negative", 2, 7, 0.05, True),    # ... with one global unit, found by the rank that holds the negative weight
-])
-def test_sharded_rcb_matches_oracle(two_gpus, oracle, wkind, dim, iters, tol, empty_last, peer):
-    check_sharded(oracle, wkind, dim, iters, tol, empty_last, peer, 2)
+    ("i32", 3, 11, 0.05, False),          # 2^11 parts: every level keeps block-private histograms (up to 12 levels)
+]
 
 
-@pytest.mark.parametrize("world", [4, 8])
-@pytest.mark.parametrize("wkind,dim,iters,tol,empty_last,peer", [
-    ("i64", 3, 10, 0.05, False, True),
-    ("f64", 3, 10, 0.05, False, True),
-    ("f64", 3, 9, 0.05, True, False),
-    ("f64lognormal", 3, 9, 0.02, False, True),
-    ("f64outlier", 2, 8, 0.05, True, True),
-    ("const", 3, 8, 0.0, False, True),
-])
-def test_sharded_rcb_matches_oracle_4_and_8_gpus(oracle, world, wkind, dim, iters, tol, empty_last, peer):
-    """The exchange layout (XCHG_DEPTH slots x world sources) and the flag protocol at world sizes above 2."""
-    _world_or_skip(world)
-    check_sharded(oracle, wkind, dim, iters, tol, empty_last, peer, world)
-
-
-def check_sharded(oracle, wkind, dim, iters, tol, empty_last, peer, world):
+def make_case(wkind, dim, iters, tol, empty_last, peer):
     rng = np.random.default_rng(11)
     n = 300_007
     k = rng.integers(0, 5, n)
     pts = (rng.random((5, dim)) * 4)[k] + rng.normal(size=(n, dim)) * 0.3
     w = {"i64": rng.integers(1, 100, n).astype(np.int64),
+         "i32": rng.integers(1, 100, n).astype(np.int32),
          "i64big": rng.integers(1, 2**40, n).astype(np.int64),
          "f64": rng.uniform(0.5, 1.5, n),
          "f64outlier": np.where(np.arange(n) == n - 77_777, 1e9, rng.uniform(0.5, 1.5, n)),
          "f64lognormal": rng.lognormal(0.0, 5.0, n),
          "f64negative": np.where(np.arange(n) == n - 99_999, -0.125, rng.uniform(0.5, 1.5, n)),
          "const": np.array(3, dtype=np.int32)}[wkind]
-    got = run_sharded((pts, w, iters, tol, False, empty_last, peer), world)
-    assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=1))
-    if wkind.startswith("f64"):  # and the reference's native f64 sums
-        assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=0))
+    return (pts, w, iters, tol, False, empty_last, peer)
+
+
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-exchange", "nccl"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_rcb_matches_oracle(oracle, world, peer):
+    """Every case of RCB_CASES at world sizes 2, 4 and 8 (the exchange layout, XCHG_DEPTH slots x world sources,
+    and the flag protocol differ in size), through the peer-memory exchange and through NCCL all-reduces."""
+    _world_or_skip(world)
+    cases = [make_case(*c, peer) for c in RCB_CASES]
+    for spec, case, got in zip(RCB_CASES, cases, run_sharded(cases, world)):
+        pts, w, iters, tol = case[:4]
+        assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=1)), spec
+        if spec[0].startswith("f64"):  # and the reference's native f64 sums
+            assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=0)), spec
 
 
 def test_sharded_rib_matches_single_gpu(two_gpus):
@@ -138,7 +139,7 @@ def test_sharded_rib_matches_single_gpu(two_gpus):
     c, s = np.cos(0.7), np.sin(0.7)
     pts = pts @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]]).T
     w = rng.integers(1, 10, n).astype(np.int64)
-    got = run_sharded((pts, w, 6, 0.05, True, False, True))
+    got = run_sharded([(pts, w, 6, 0.05, True, False, True)])[0]
     dev = torch.device("cuda", 0)
     part = torch.empty(n, dtype=torch.int64, device=dev)
     coupe_b200.Rib(6, 0.05).partition(part, (torch.from_numpy(pts).to(dev), torch.from_numpy(w).to(dev)))

@@ -123,6 +123,14 @@ def test_mewe_errors(tools, tmp_path):
         tools.read_weights(p)
     with pytest.raises(BackendError):
         tools.read_weights(str(tmp_path / "missing"))
+    # a corrupt count (n * criteria * 8 overflows to a small number): an error, not a wild read
+    for n in (2**61, 2**64 - 1, 2**40):
+        open(p, "wb").write(b"MeWe" + bytes([1, 0, 1, 0]) + struct.pack("<Q", n) + bytes(64))
+        with pytest.raises(BackendError):
+            tools.read_weights(p)
+        open(p, "wb").write(b"MePe" + struct.pack("<Q", n) + bytes(64))
+        with pytest.raises(BackendError):
+            tools.read_partition(p)
 
 
 def test_mepe_golden_bytes(tools, tmp_path):
