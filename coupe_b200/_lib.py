@@ -43,7 +43,8 @@ class Stats(C.Structure):
                 ("weight_shift", C.c_int32), ("host_syncs", C.c_uint32), ("flag_waits", C.c_uint32),
                 ("peer_exchange", C.c_uint32), ("carry_free", C.c_uint32), ("weight_wide", C.c_uint32),
                 ("weight_rescales", C.c_uint32), ("matrix", C.c_double * 9), ("dense_sweep_ms", C.c_double),
-                ("refine_sweep_ms", C.c_double), ("refine_points", C.c_uint64), ("exchange_wait_ms", C.c_double)]
+                ("refine_sweep_ms", C.c_double), ("refine_points", C.c_uint64), ("exchange_wait_ms", C.c_double),
+                ("deferred_levels", C.c_uint32), ("list_refine_sweeps", C.c_uint32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "matrix"}

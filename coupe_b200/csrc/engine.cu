@@ -223,7 +223,8 @@ struct coupe_b200_ctx {
   Buf host_w, host_ids, host_pts;  // host path: device copies of the caller's weights / (RIB) points, compact ids
   Buf xcols, ids, w32, node_rt, rfast, part_w, part_min, hist_w, hist_min, nodes_a, nodes_b, table_a, table_b, thi_a, thi_b,
       tsp_a, tsp_b, nsh_a, nsh_b, target, rtable, gp,
-      tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial;
+      tr_visited, tr_split, tr_wl, tr_sum, tr_iters, mom_partial,
+      def_rec, def_slot, def_count, target_first, rpart_w, rpart_min;  // deferred points (rcb_kernels.cuh)
   uint32_t *h_pinned = nullptr;  // pinned host scratch (64 words)
   volatile unsigned long long *h_flags = nullptr;  // mapped pinned: one word per pass, written by the GPU
   unsigned long long *d_flags = nullptr;           // device view of h_flags
@@ -243,6 +244,7 @@ struct coupe_b200_ctx {
   int table_rep_max = 3; // experiments: cap on the bank-private copies of the per-parent table (log2)
   int carve_fit = 1;     // keep the dense sweeps under the 196 KB shared-memory carve-out when the tables allow it
   int sample_w_opt = 1;  // f64 weights: max |w| from a sample, verified by the root sweep
+  int defer_opt = 1;     // undecided levels: the next dense sweep lists the points of the undecided bins (no rescan of idx)
   std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
   std::vector<int> event_kind;      // 0 dense, 1 refine
   std::vector<int> event_level;     // tree level of the sweep
@@ -265,7 +267,7 @@ size_t sweep_smem_bytes(int level, int rep_log2, bool aux) {
   size_t b = HIST_BYTES + (parents << rep_log2) * sizeof(float4);
   // the rarely read values: split positions, bracket ends, per-node shifts (f64 weights, wide form)
   if (aux) b += parents * 2 * sizeof(float) + ((((size_t)2 << level) + 15) & ~(size_t)15);
-  return b;
+  return b + 128;  // the per-warp counters of deferred points (last 128 bytes)
 }
 // Shared memory is carved out of the SM's 228 KB in steps (..., 164, 196, 228 KB, 1 KB of each reserved by the
 // system); what is left is the L1 cache and the staging of global loads.  A sweep that needs a few bytes more
@@ -334,6 +336,8 @@ void prepare_funcs(coupe_b200_ctx *c) {
   SETREF(WIN_F64);
   SETREF(WIN_CONST);
 #undef SETREF
+  SETATTR(defer_refine_kernel<WIN_I32>);
+  SETATTR(defer_refine_kernel<WIN_CONST>);
 #undef SETALL
 #undef SETATTR
   c->funcs_ready = true;
@@ -348,6 +352,7 @@ struct FirstPlan {
   bool aux_in_smem;    // ... and the rarely read per-parent values with it
   int table_rep_log2;  // ... replicated 2^this times (bank-private copies at the deep levels)
   size_t bytes;        // dynamic shared memory
+  size_t def_off;      // offset of the deferred-point counter in it (smem mode)
 };
 
 FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
@@ -374,6 +379,7 @@ FirstPlan plan_first(const coupe_b200_ctx *c, int level) {
       while (p.table_rep_log2 > 0 && sweep_smem_bytes(level, p.table_rep_log2, true) > c->max_smem) --p.table_rep_log2;
     }
     p.bytes = sweep_smem_bytes(level, p.table_rep_log2, p.aux_in_smem);
+    p.def_off = p.bytes - 128;
     if (p.bytes + c->smem_pad <= c->max_smem) p.bytes += c->smem_pad;
     if (p.bytes > c->max_smem) p.smem = false;
   }
@@ -463,6 +469,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   c->nsh_a.ensure(max_nodes * 2 * sizeof(short));
   c->nsh_b.ensure(max_nodes * 2 * sizeof(short));
   c->target.ensure(max_nodes * sizeof(uint32_t));
+  c->target_first.ensure(max_nodes * sizeof(uint32_t));
   c->node_rt.ensure(max_nodes * sizeof(uint2));
   c->rfast.ensure(max_nodes * sizeof(float2));
   c->gp.ensure(sizeof(GlobalParams));
@@ -484,19 +491,46 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   float *x[3] = {c->xcols.as<float>(), c->xcols.as<float>() + npad, c->xcols.as<float>() + 2 * npad};
   void *ids = c->ids.p;
 
+  const size_t ngroups = (n + 3) / 4;
+  const int sweep_grid =
+      std::max(1, (int)std::min<size_t>((size_t)c->num_sms, (ngroups + SWEEP_THREADS - 1) / SWEEP_THREADS));
+  // points one block of a dense sweep processes at most (grid-stride over groups of four, plus the tail)
+  const size_t block_points = ((n / 4) / ((size_t)sweep_grid * SWEEP_THREADS) + 1) * SWEEP_THREADS * 4 + 4;
+  // Deferred points (rcb_kernels.cuh): per-block lists with room for every point the block sweeps, so a list
+  // cannot overflow whatever share of a node sits in the bin under refinement.  20 bytes per point of scratch;
+  // without it (allocation failure, option "defer" 0) undecided levels are refined by scanning the idx words.
+  const size_t warp_points = block_points / DEFER_LISTS + 4;  // ... and one of its warps (every thread runs the same number of groups, +-1)
+  bool defer_call = c->defer_opt && L >= 2 && n < ((size_t)1 << 32);
+  if (defer_call) {
+    try {
+      c->def_rec.ensure((size_t)sweep_grid * DEFER_LISTS * warp_points * sizeof(uint4));
+      c->def_slot.ensure((size_t)sweep_grid * DEFER_LISTS * warp_points * sizeof(uint32_t));
+      c->def_count.ensure((size_t)c->num_sms * DEFER_LISTS * sizeof(uint32_t));
+      c->rpart_w.ensure((size_t)c->num_sms * nb_smem * 8);
+      c->rpart_min.ensure((size_t)c->num_sms * nb_smem * 4);
+    } catch (const CudaFail &f) {
+      if (f.err != cudaErrorMemoryAllocation) throw;
+      cudaGetLastError();
+      c->def_rec.release();
+      c->def_slot.release();
+      defer_call = false;
+    }
+  }
+
   // ---- global point count ---------------------------------------------------
   unsigned long long n_global = n;
   bool any_rank_has_array_weights = w_dev != nullptr;
   if (c->world > 1) {  // a rank with an empty shard may not know whether weights are per point
     unsigned long long *d = reinterpret_cast<unsigned long long *>(c->hist_w.p);
-    unsigned long long h[2] = {n_global, w_dev ? 1ull : 0ull};
-    CU(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, st));
-    R.allreduce(d, 2, ncclUint64, ncclSum);
-    CU(cudaMemcpyAsync(c->h_pinned, d, 16, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[3] = {n_global, w_dev ? 1ull : 0ull, defer_call ? 1ull : 0ull};
+    CU(cudaMemcpyAsync(d, h, 24, cudaMemcpyHostToDevice, st));
+    R.allreduce(d, 3, ncclUint64, ncclSum);
+    CU(cudaMemcpyAsync(c->h_pinned, d, 24, cudaMemcpyDeviceToHost, st));
     R.sync();
-    memcpy(h, c->h_pinned, 16);
+    memcpy(h, c->h_pinned, 24);
     n_global = h[0];
     any_rank_has_array_weights = h[1] != 0;
+    defer_call = h[2] == (unsigned long long)c->world;  // every rank must run the same pass sequence
   }
   S.n_global = n_global;
   // i32 column read by the sweeps below the root: narrowed f64 / i64 weights, or an aligned copy
@@ -601,6 +635,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   short *nsh_cur = c->nsh_a.as<short>(), *nsh_next = c->nsh_b.as<short>();
   float4 *rtable = c->rtable.as<float4>();
   uint32_t *target = c->target.as<uint32_t>();
+  uint32_t *target_first = c->target_first.as<uint32_t>();
   // per-point f64 weights: the fixed-point form and scale come from statistics of a sample of the weights;
   // the root sweep computes the true ones and the walk of the root asks for another root pass when they differ
   const bool verify_form = wtype == WT_F64 && !w_is_const;
@@ -611,9 +646,6 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
   };
   enqueue_init_root(0);
 
-  const size_t ngroups = (n + 3) / 4;
-  const int sweep_grid =
-      std::max(1, (int)std::min<size_t>((size_t)c->num_sms, (ngroups + SWEEP_THREADS - 1) / SWEEP_THREADS));
   unsigned long long *hist_w = c->hist_w.as<unsigned long long>();
   uint32_t *hist_min = c->hist_min.as<uint32_t>();
   int *w32 = narrow_w ? c->w32.as<int>() : nullptr;
@@ -728,11 +760,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     size_t rtb_;
     const uint64_t s = seq++;
     c->h_flags[flag_slot(s)] = 0;
-    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, nsh_next, target, node_rt, rtable,
+    WalkArgs wa{cur, nxt, hist_w, hist_min, gp, tab_next, thi_next, tsp_next, nsh_next, target, target_first, node_rt, rtable,
                 tr, tolerance, level, k, D, first, level == L - 1, w_is_const, k0, rank_limit, guard,
                 plan_first(c, level + 1).k, rfast, refine_cap(level, rts_, rtb_), c->kmax_refine,
-                verify_form ? 1 : 0,
-                (unsigned long long)(((n / 4) / ((size_t)sweep_grid * SWEEP_THREADS) + 1) * SWEEP_THREADS * 4 + 4),
+                verify_form ? 1 : 0, (unsigned long long)block_points,
                 c->d_flags + flag_slot(s), make_xchg(s)};
     const size_t bytes = ((size_t)2 << k) * 12;
     const uint32_t nodes = 1u << level;
@@ -743,9 +774,10 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     R.launched(1);
     return s;
   };
-  // the dense first pass of `level`; kprev = bins of the level before
-  auto enqueue_first_pass = [&](int level, int kprev, const uint32_t *guard) {
-    NvtxRange range("rcb level %d: dense pass%s", level, guard ? " (optimistic)" : "");
+  // the dense sweep of `level`; kprev = bins of the level before; defer: points whose parent is still
+  // undecided are listed instead of binned (the sweep then needs no guard)
+  auto enqueue_dense = [&](int level, int kprev, const uint32_t *guard, bool defer) {
+    NvtxRange range("rcb level %d: dense sweep%s", level, guard ? " (optimistic)" : defer ? " (deferring)" : "");
     const int axis = level % D, prev_axis = (level + D - 1) % D;
     const FirstPlan plan = plan_first(c, level);
     const int k = plan.k;
@@ -775,6 +807,13 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     sa.one = 1;
     sa.table_rep_log2 = plan.table_rep_log2;
     sa.aux_in_smem = plan.aux_in_smem ? 1 : 0;
+    if (defer) {
+      sa.def_rec = c->def_rec.as<uint4>();
+      sa.def_slot = c->def_slot.as<uint32_t>();
+      sa.def_count = c->def_count.as<uint32_t>();
+      sa.def_seg = (uint32_t)warp_points;
+    }
+    sa.def_smem_off = (uint32_t)plan.def_off;
     if (!plan.smem) {
       launch_pdl(fill_hist_kernel, (nb + 255) / 256, 256, 0, st, hist_w, hist_min, nb, guard);
       R.launched();
@@ -785,14 +824,92 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     time_end();
     R.launched();
     S.dense_sweeps += 1;
+  };
+  // partial histograms of the dense sweep of `level` -> level histogram -> walk
+  auto enqueue_reduce_walk = [&](int level, const uint32_t *guard) {
+    const FirstPlan plan = plan_first(c, level);
+    const uint32_t nb = 1u << (level + plan.k);
     if (plan.smem) {
-      launch_pdl(reduce_partials_kernel, (nb + 31) / 32, 256, 0, st, sa.part_w, sa.part_min, sweep_grid, nb, hist_w,
-                 hist_min, guard, make_xchg(seq));
+      launch_pdl(reduce_partials_kernel, (nb + 31) / 32, 256, 0, st, (const long long *)c->part_w.as<long long>(),
+                 (const uint32_t *)c->part_min.as<uint32_t>(), sweep_grid, nb, hist_w, hist_min,
+                 guard, make_xchg(seq));
       R.launched();
     }
     allreduce_hist(nb);
     if (level == 0 && verify_form) R.allreduce(gp->wstat_true, WS_N, ncclUint64, ncclMax);
-    return enqueue_walk(level, k, k, 1, 0, guard);
+    return enqueue_walk(level, plan.k, plan.k, 1, 0, guard);
+  };
+  auto enqueue_first_pass = [&](int level, int kprev, const uint32_t *guard) {
+    enqueue_dense(level, kprev, guard, false);
+    return enqueue_reduce_walk(level, guard);
+  };
+  // --- deferred points: the level below an undecided one has listed the points of the undecided bins ---
+  auto can_defer = [&](int level_next) {
+    return defer_call && level_next < L && plan_first(c, level_next).smem && (win == WIN_I32 || win == WIN_CONST);
+  };
+  auto defer_args = [&](int level_next) {
+    DeferArgs d{};
+    d.rec = c->def_rec.as<uint4>();
+    d.slot0 = c->def_slot.as<uint32_t>();
+    d.count = c->def_count.as<uint32_t>();
+    d.seg = (uint32_t)warp_points;
+    d.kslot = plan_first(c, level_next).k;
+    d.node_rt = node_rt;
+    d.rtable = rtable;
+    d.rfast = rfast;
+    d.part_w = c->rpart_w.as<long long>();
+    d.part_min = c->rpart_min.as<uint32_t>();
+    d.one = 1;
+    d.gp = gp;
+    d.idx = ids;
+    d.target_first = target_first;
+    return d;
+  };
+  // one refinement pass of `level` over the list written by the dense sweep of level + 1
+  auto enqueue_defer_refine_round = [&](int level, int k0, uint32_t unresolved) {
+    NvtxRange range("rcb level %d: refinement pass over the deferred points, %u undecided nodes", level, unresolved);
+    bool rts;
+    size_t rt_bytes;
+    const uint32_t cap = refine_cap(level, rts, rt_bytes);  // (the walk ranks with the same capacity)
+    const int kr = refine_bits(unresolved, cap, c->kmax_refine);
+    const uint32_t limit = std::min<uint32_t>(unresolved, cap >> kr);
+    DeferArgs da = defer_args(level + 1);
+    da.nslots = limit << kr;
+    da.rank_limit = limit;
+    da.k = kr;
+    time_begin(1, level);
+    if (win == WIN_I32) launch_pdl(defer_refine_kernel<WIN_I32>, sweep_grid, SWEEP_THREADS, (size_t)da.nslots * 12, st, da);
+    else launch_pdl(defer_refine_kernel<WIN_CONST>, sweep_grid, SWEEP_THREADS, (size_t)da.nslots * 12, st, da);
+    time_end();
+    launch_pdl(reduce_partials_kernel, (da.nslots + 31) / 32, 256, 0, st, (const long long *)da.part_w,
+               (const uint32_t *)da.part_min, sweep_grid, da.nslots, hist_w, hist_min, (const uint32_t *)nullptr,
+               make_xchg(seq));
+    R.launched(2);
+    S.refine_sweeps += 1;
+    S.list_refine_sweeps += 1;
+    allreduce_hist(da.nslots);
+    return enqueue_walk(level, kr, k0, 0, limit, nullptr);
+  };
+  // every split of the level above `level_next` is decided (tab_cur / tsp_cur are final): the deferred
+  // points take their child and join level_next's partial histograms
+  auto enqueue_fixup = [&](int level_next) {
+    NvtxRange range("rcb level %d: deferred points take their child", level_next);
+    const FirstPlan plan = plan_first(c, level_next);
+    const uint32_t nb = 1u << (level_next + plan.k);
+    DeferArgs da = defer_args(level_next);
+    da.table = tab_cur;
+    da.table_split = tsp_cur;
+    da.row_w = c->part_w.as<unsigned long long>();
+    da.row_min = c->part_min.as<uint32_t>();
+    da.row_stride = nb;
+    if (win == WIN_I32) {
+      if (idx16) launch_pdl(defer_fixup_kernel<WIN_I32, uint16_t>, sweep_grid, SWEEP_THREADS, 0, st, da);
+      else launch_pdl(defer_fixup_kernel<WIN_I32, uint32_t>, sweep_grid, SWEEP_THREADS, 0, st, da);
+    } else {
+      if (idx16) launch_pdl(defer_fixup_kernel<WIN_CONST, uint16_t>, sweep_grid, SWEEP_THREADS, 0, st, da);
+      else launch_pdl(defer_fixup_kernel<WIN_CONST, uint32_t>, sweep_grid, SWEEP_THREADS, 0, st, da);
+    }
+    R.launched();
   };
   auto enqueue_refine_round = [&](int level, int k0, uint32_t unresolved) {
     NvtxRange range("rcb level %d: refinement pass, %u undecided nodes", level, unresolved);
@@ -855,6 +972,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     const bool can_speculate = !(level == 0 && ((w32 && wtype == WT_I64) || verify_form));
     advance_level();
     bool speculated = false;
+    bool spec_deferred = false;  // the dense sweep of level + 1 is enqueued, and it defers
     uint64_t next_pending = 0;
     int win_root = win;
     const void *wp_root = wp;
@@ -863,8 +981,18 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       wp = w32;
     }
     if (can_speculate) {
-      if (level + 1 < L) next_pending = enqueue_first_pass(level + 1, k, guard_ptr);
-      else enqueue_emit(k, guard_ptr);
+      if (level + 1 < L) {
+        spec_deferred = can_defer(level + 1);
+        if (spec_deferred) {
+          // the sweep runs whatever the walk of this level says; only its reduce + walk are optimistic
+          enqueue_dense(level + 1, k, nullptr, true);
+          next_pending = enqueue_reduce_walk(level + 1, guard_ptr);
+        } else {
+          next_pending = enqueue_first_pass(level + 1, k, guard_ptr);
+        }
+      } else {
+        enqueue_emit(k, guard_ptr);
+      }
       speculated = true;
     }
     uint32_t unresolved = wait_flag(pending);
@@ -902,7 +1030,22 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
         wp = w32;
       }
     }
-    if (unresolved > 0) {
+    if (unresolved > 0 && (speculated ? spec_deferred : can_defer(level + 1))) {
+      // Deferred refinement: the dense sweep of level + 1 lists the points of the undecided bins; the
+      // refinement passes of this level read that list, then the listed points take their child.
+      if (!speculated) enqueue_dense(level + 1, k, nullptr, true);
+      S.deferred_levels += 1;
+      advance_level();  // back to this level's tables
+      int rounds = 0;
+      while (unresolved > 0) {
+        if (++rounds > 100000) return COUPE_ERR_CRASH;  // cannot happen: f32 brackets shrink
+        unresolved = wait_flag(enqueue_defer_refine_round(level, k, unresolved));
+      }
+      advance_level();
+      enqueue_fixup(level + 1);
+      next_pending = enqueue_reduce_walk(level + 1, nullptr);
+      speculated = true;
+    } else if (unresolved > 0) {
       // the optimistic pass (if any) returned at once on the device; refine this level, then redo it
       if (speculated && level + 1 < L) {
         S.dense_sweeps -= 1;
@@ -1388,6 +1531,7 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "peer_exchange") c->use_xchg_opt = value != 0;
   else if (s == "sample_weights") c->sample_w_opt = value != 0;
   else if (s == "carve_fit") c->carve_fit = value != 0;
+  else if (s == "defer") c->defer_opt = value != 0;
   else if (s == "smem_pad") c->smem_pad = (int)std::max<int64_t>(0, std::min<int64_t>(32768, value));
   else if (s == "table_rep_max") c->table_rep_max = (int)std::max<int64_t>(0, std::min<int64_t>(3, value));
   else return COUPE_ERR_NOT_FOUND;

@@ -487,6 +487,12 @@ struct SweepArgs {
   int aux_in_smem;           // the rarely read per-parent / per-node values (split position, bracket end, f64 shift) are staged too
   uint32_t one;              // 1, from the host: a literal 1 turns `red.shared.add` into ATOMS.POPC.INC,
                              // which is several times slower than ATOMS.ADD on scattered addresses
+  // Deferred points (see "Deferred points" below): null / 0 when the pass does not defer
+  uint4 *def_rec;            // [grid * 32][def_seg] records {point index, previous-axis coordinate, this-axis coordinate, weight}
+  uint32_t *def_slot;        // [grid * 32][def_seg] histogram slot of the point if it goes LEFT
+  uint32_t *def_count;       // [grid * 32] records appended by each warp
+  uint32_t def_seg;          // records one warp may append (the points it sweeps)
+  uint32_t def_smem_off;     // byte offset of the 32 per-warp record counters in dynamic shared memory
 };
 
 // Exact bin of x in the bracket [lo, hi]: k dyadic bisection steps with the
@@ -591,10 +597,17 @@ struct RawW4<WIN_CONST> {
   __device__ __forceinline__ void load(const void *, size_t, bool) {}
   __device__ __forceinline__ void get(long long (&o)[4]) const { o[0] = o[1] = o[2] = o[3] = 1; }
   __device__ __forceinline__ void raw(double (&)[4]) const {}
+  __device__ __forceinline__ void zero(int) {}
 };
 template <>
 struct RawW4<WIN_I32> {
   int4 v;
+  __device__ __forceinline__ void zero(int j) {  // (j is a constant after unrolling)
+    if (j == 0) v.x = 0;
+    if (j == 1) v.y = 0;
+    if (j == 2) v.z = 0;
+    if (j == 3) v.w = 0;
+  }
   __device__ __forceinline__ void load(const void *w, size_t i0, bool vec) {
     const int *p = static_cast<const int *>(w) + i0;
     if (vec) v = __ldcs(reinterpret_cast<const int4 *>(p));
@@ -622,6 +635,7 @@ struct RawW4<WIN_I64> {
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
   }
   __device__ __forceinline__ void raw(double (&)[4]) const {}
+  __device__ __forceinline__ void zero(int) {}
 };
 template <>
 struct RawW4<WIN_F64> {
@@ -640,6 +654,7 @@ struct RawW4<WIN_F64> {
   __device__ __forceinline__ void raw(double (&o)[4]) const {  // quantised by the sweep (quantise_f64)
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
   }
+  __device__ __forceinline__ void zero(int) {}
 };
 
 // idx words of four consecutive points: 16-bit when every level of the call
@@ -728,6 +743,15 @@ __device__ __forceinline__ void hist_add_generic(uint32_t lo_addr, long long w, 
   if (key < lds_min_of(lo_addr)) reds_min_of(lo_addr, key);
 }
 
+// Deferred points are appended to one list per WARP of the sweep; a thread takes the places of all
+// the points it defers from one group with one returning shared-memory atomic.  Returns the index of
+// the caller's first record.
+constexpr int DEFER_LISTS = SWEEP_THREADS / 32;
+__device__ __forceinline__ size_t defer_append(uint32_t *s_cnt, uint32_t seg, uint32_t count) {
+  const uint32_t warp = threadIdx.x >> 5;
+  return ((size_t)blockIdx.x * DEFER_LISTS + warp) * seg + atomicAdd(s_cnt + warp, count);
+}
+
 // TSM: the per-parent table is staged in shared memory (always in SMEM mode).
 template <int WIN, bool SMEM, bool ROOT, bool TSM, class IDX>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_constant__ SweepArgs a) {
@@ -752,12 +776,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   float *s_thi = s_split + (aux ? nparents : 0);
   short *s_nshift = reinterpret_cast<short *>(s_thi + (aux ? nparents : 0));  // [nodes of this level], wide f64 only
   constexpr bool WIDE_LEVEL = !ROOT && WIN == WIN_F64;  // below the root f64 weights are read only in the wide form
+  // Deferred points: a point of the ONE bin an undecided bisection of the level above narrowed down to does
+  // not know its child yet (its parent's split position is NaN in the table).  It is appended to the block's
+  // list with what the refinement of the parent and the later fix-up need, and contributes nothing here.
+  constexpr bool CAN_DEFER = !ROOT && SMEM && (WIN == WIN_I32 || WIN == WIN_CONST);
+  const bool defer_on = CAN_DEFER && a.def_rec != nullptr;
+  uint32_t *s_defcnt = reinterpret_cast<uint32_t *>(smem_raw + (CAN_DEFER ? a.def_smem_off : 0));
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i + 1 <= nwords; i += blockDim.x) {  // (i < nwords; written so for nwords == 0)
       s_lo[i] = 0;
       s_hi[i] = 0;
       s_min[i] = (uint32_t)SKEY_EMPTY;
     }
+    if (defer_on && threadIdx.x < DEFER_LISTS) s_defcnt[threadIdx.x] = 0;
   }
   // the histogram was cleared while the previous kernel (the walk that wrote the tables) drained
   pdl_wait();
@@ -797,14 +828,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 
-  auto process = [&](const Group4<WIN, ROOT, IDX> &cur, size_t g) {
+  auto process = [&](Group4<WIN, ROOT, IDX> &cur, size_t g) {
     const size_t i0 = g * 4;
     uint32_t pv[4] = {0, 0, 0, 0};
     if (!ROOT) cur.pv.get(pv);
-    const float x[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
+    float x[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
     uint32_t slot[4], pk[4], sel[4];
     bool slow = false;  // some point is within rounding of a bin boundary
-    bool hit = false;   // some point sits in the bin its parent's refined split fell into
+    bool hit = false;   // some point sits in the bin its parent's refined (or still undecided) split fell into
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t p = pv[j] >> kprev;
@@ -824,17 +855,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       pk[j] = p << (k + 1);
       slot[j] = __float_as_uint(tf);
     }
-    if (!ROOT && hit) {  // the points of a refined bin compare their previous-axis coordinate with the split
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t p = pv[j] >> kprev;
-        const uint32_t tw = __float_as_uint(TSM ? s_table[(p << rlog) + rep_lane].w : __ldg(&a.table[p]).w);
-        if (2 * pv[j] + 1 == tw) {
-          const float split = aux ? s_split[p] : __ldg(a.table_split + p);
-          sel[j] = !(__ldg(a.xp + i0 + j) < split) ? sel_right : sel_left;
-        }
-      }
-    }
     if (slow) {  // rare: redo the test per point, exact k-step descend where it fails
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -845,6 +865,47 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
         const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
         if (!(fabsf(fr - 0.5f) < e.z))
           slot[j] = 0x4B000000u + descend_exact(x[j], e.x, aux ? s_thi[p] : __ldg(a.table_hi + p), k);
+      }
+    }
+    uint32_t defm = 0;  // points of this group that were deferred
+    if (!ROOT && hit) {  // the points of a refined bin compare their previous-axis coordinate with the split
+      // (the gathers of the four points are issued together: a branch per point would pay their latency in turn)
+      float xpv[4], spl[4];
+      uint32_t hm = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t p = pv[j] >> kprev;
+        const uint32_t tw = __float_as_uint(TSM ? s_table[(p << rlog) + rep_lane].w : __ldg(&a.table[p]).w);
+        const bool h = 2 * pv[j] + 1 == tw;
+        hm |= (h ? 1u : 0u) << j;
+        xpv[j] = 0.f;
+        spl[j] = 0.f;
+        if (h) {
+          xpv[j] = __ldg(a.xp + i0 + j);
+          spl[j] = aux ? s_split[p] : __ldg(a.table_split + p);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (hm & (1u << j)) {
+          if (CAN_DEFER && spl[j] != spl[j]) defm |= 1u << j;  // the parent's bisection is still undecided
+          else sel[j] = !(xpv[j] < spl[j]) ? sel_right : sel_left;
+        }
+      }
+      if (CAN_DEFER && defm) {
+        long long wj[4];
+        cur.w.get(wj);
+        size_t pos = defer_append(s_defcnt, a.def_seg, (uint32_t)__popc(defm));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (defm & (1u << j)) {
+            a.def_rec[pos] = make_uint4((uint32_t)(i0 + j), __float_as_uint(xpv[j]), __float_as_uint(x[j]), (uint32_t)wj[j]);
+            a.def_slot[pos] = slot[j] + pk[j] + sel_left;
+            ++pos;
+            cur.w.zero(j);
+            x[j] = __int_as_float(SKEY_EMPTY);  // its key is SKEY_EMPTY: lowers no minimum
+          }
+        }
       }
     }
 #pragma unroll
@@ -935,6 +996,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
         const int key = f2skey(x[j]);
         if (key < mn[j]) reds_min_of(addr[j], key);
       }
+      if (WIN == WIN_CONST && CAN_DEFER && defm) {  // a deferred point is not counted here
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (defm & (1u << j)) reds_add(addr[j], 0u - a.one);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) accumulate_global(a.hist_w, a.hist_min, slot[j], w[j], f2key(x[j]));
@@ -963,6 +1029,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
       const float x = a.x[i];
       const uint32_t slot = slot_exact(a, pv, x, i, ROOT);
       static_cast<IDX *>(a.idx)[i] = (IDX)slot;
+      if (defer_on) {
+        const uint32_t p = pv >> kprev;
+        const float split = a.table_split[p];
+        if (2 * pv + 1 == __float_as_uint(a.table[p].w) && split != split) {
+          // (slot_exact compared with the NaN: it chose the right child)
+          const size_t pos = defer_append(s_defcnt, a.def_seg, 1u);
+          a.def_rec[pos] = make_uint4((uint32_t)i, __float_as_uint(a.xp[i]), __float_as_uint(x),
+                                      (uint32_t)load_w1<WIN>(a.w, i));
+          a.def_slot[pos] = slot - kbit;
+          continue;
+        }
+      }
       long long w = load_w1<WIN>(a.w, i);
       if (WIN == WIN_F64) {
         const double r = static_cast<const double *>(a.w)[i];
@@ -997,6 +1075,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   }
   if (SMEM) {
     __syncthreads();
+    if (defer_on && threadIdx.x < DEFER_LISTS) a.def_count[blockIdx.x * DEFER_LISTS + threadIdx.x] = s_defcnt[threadIdx.x];
     long long *pw = a.part_w + (size_t)blockIdx.x * nb;
     uint32_t *pm = a.part_min + (size_t)blockIdx.x * nb;
     const int ncopy = 1 << clog;
@@ -1344,6 +1423,171 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_refine_kernel(const __
   }
 }
 
+// ---------------------------------------------------------------------------
+// Deferred points.  When some bisections of level l are still undecided after the dense pass, the
+// dense sweep of level l+1 runs all the same: the children's brackets on the next axis are known
+// (inherited), every point outside the single bin an undecided bracket shrank to knows its side,
+// and the points inside that bin (a few percent) are APPENDED to a per-block list instead of being
+// binned: {index, coordinate on level l's axis, coordinate on level l+1's axis, weight} and the
+// level-(l+1) slot the point takes if it goes left.  The refinement passes of level l then read
+// that dense list (defer_refine_kernel) instead of scanning every idx word and gathering, and once
+// every split of level l is decided defer_fixup_kernel gives the listed points their child: it
+// writes their idx words and adds them to level l+1's partial histograms (the rows the sweep wrote).
+// Integer sums: the result does not depend on the order of the list.
+// ---------------------------------------------------------------------------
+struct DeferArgs {
+  const uint4 *rec;          // [grid * 32][seg]: one list per warp of the sweep that wrote them
+  const uint32_t *slot0;     // [grid * 32][seg]
+  const uint32_t *count;     // [grid * 32]
+  uint32_t seg;
+  int kslot;                 // bins (log2) of level l+1's dense pass: slot0 = (parent << (kslot + 1)) + bin
+  // refinement of level l
+  const uint2 *node_rt;      // per node: {idx value of the bin under refinement, rank}; TARGET_NONE if resolved
+  const float4 *rtable;      // per node: {lo, hi, hi inclusive, -}
+  const float2 *rfast;       // per node: {2^k / width, 0.5 - eps} of the refinement bracket
+  long long *part_w;         // per-block partial histograms [grid][nslots]
+  uint32_t *part_min;
+  uint32_t nslots, rank_limit;
+  int k;                     // bins (log2) per undecided node of this refinement pass
+  uint32_t one;
+  GlobalParams *gp;
+  // fix-up
+  void *idx;                 // idx words of level l+1
+  const float4 *table;       // per parent (node of level l): final split word in .w
+  const float *table_split;  // per parent: final split position
+  const uint32_t *target_first;  // per parent: idx word (level l) of the bin its deferred points came from
+  unsigned long long *row_w;     // level l+1's partial histograms [grid][row_stride], written by the dense sweep
+  uint32_t *row_min;
+  uint32_t row_stride;
+};
+
+// Four records per lane are in flight at a time: the lists are short (a few hundred records per warp)
+// and every record starts a chain of dependent loads, so the kernels are latency-bound otherwise.
+constexpr int DEFER_UNROLL = 4;
+
+template <int WIN>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) defer_refine_kernel(const __grid_constant__ DeferArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t nslots = a.nslots;
+  uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
+  uint32_t *s_hi = s_lo + nslots;
+  uint32_t *s_min = s_hi + nslots;
+  for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+    s_lo[i] = 0;
+    s_hi[i] = 0;
+    s_min[i] = KEY_EMPTY;
+  }
+  pdl_wait();
+  __syncthreads();
+  const uint32_t lo_base = smem_addr(s_lo);
+  const uint32_t hi_off = nslots * 4, min_off = nslots * 8;
+  const int k = a.k;
+  unsigned long long matched = 0;
+  // warp w of block b reads the list of warp w of block b of the sweep that wrote it (same grid)
+  const size_t list = (size_t)blockIdx.x * DEFER_LISTS + (threadIdx.x >> 5);
+  const uint32_t cnt = a.count[list];
+  const size_t base = list * a.seg;
+  for (uint32_t e0 = threadIdx.x & 31; e0 < cnt; e0 += 32 * DEFER_UNROLL) {
+    uint4 r[DEFER_UNROLL];
+    uint32_t p[DEFER_UNROLL];
+    uint2 rt[DEFER_UNROLL];
+    float4 br[DEFER_UNROLL];
+    float2 f[DEFER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DEFER_UNROLL; ++u) {
+      const uint32_t e = e0 + 32 * u;
+      p[u] = 0;
+      r[u] = make_uint4(0, 0, 0, 0);
+      if (e < cnt) {
+        r[u] = __ldg(a.rec + base + e);
+        p[u] = __ldg(a.slot0 + base + e) >> (a.kslot + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DEFER_UNROLL; ++u) {
+      rt[u] = __ldg(&a.node_rt[p[u]]);
+      br[u] = __ldg(&a.rtable[p[u]]);
+      f[u] = __ldg(&a.rfast[p[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < DEFER_UNROLL; ++u) {
+      if (e0 + 32 * u >= cnt) continue;
+      if (rt[u].x == TARGET_NONE || rt[u].y >= a.rank_limit) continue;  // decided by an earlier pass, or waits for a later one
+      const float x = __uint_as_float(r[u].y);
+      const bool in = !(x < br[u].x) && (x < br[u].y || (br[u].z != 0.f && x <= br[u].y));
+      if (!in) continue;
+      const float t = __fmul_rn(__fsub_rn(x, br[u].x), f[u].x);
+      const float tf = __fadd_rd(t, 8388608.f);
+      const float fr = __fsub_rn(t, __fsub_rn(tf, 8388608.f));
+      uint32_t bin = __float_as_uint(tf) & 0x7FFFFFu;
+      if (!(fabsf(fr - 0.5f) < f[u].y)) bin = descend_exact(x, br[u].x, br[u].y, k);
+      const long long w = WIN == WIN_CONST ? 1ll : (long long)(int)r[u].w;
+      accumulate_smem<WIN>(lo_base + ((rt[u].y << k) + bin) * 4, hi_off, min_off, w, f2key(x), a.one);
+      ++matched;
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) matched += __shfl_xor_sync(0xffffffffu, matched, s);
+  if ((threadIdx.x & 31) == 0 && matched) atomicAdd(&a.gp->refine_points, matched);
+  __syncthreads();
+  long long *pw = a.part_w + (size_t)blockIdx.x * nslots;
+  uint32_t *pm = a.part_min + (size_t)blockIdx.x * nslots;
+  for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+    pw[i] = (long long)(((unsigned long long)s_hi[i] << 32) + s_lo[i]);
+    pm[i] = s_min[i];
+  }
+}
+
+// Every split of level l is decided: the deferred points take their child, their idx word of level
+// l+1, and their place in level l+1's histogram: block b adds its points to row b of the partial
+// histograms (the row the same block of the dense sweep wrote; L2 atomics, spread over the rows).
+template <int WIN, class IDX>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) defer_fixup_kernel(const __grid_constant__ DeferArgs a) {
+  pdl_wait();
+  const size_t list = (size_t)blockIdx.x * DEFER_LISTS + (threadIdx.x >> 5);
+  const uint32_t cnt = a.count[list];
+  const size_t base = list * a.seg;
+  const uint32_t kbit = 1u << a.kslot;
+  unsigned long long *row_w = a.row_w + (size_t)blockIdx.x * a.row_stride;
+  uint32_t *row_min = a.row_min + (size_t)blockIdx.x * a.row_stride;
+  for (uint32_t e0 = threadIdx.x & 31; e0 < cnt; e0 += 32 * DEFER_UNROLL) {
+    uint4 r[DEFER_UNROLL];
+    uint32_t s0[DEFER_UNROLL], tw[DEFER_UNROLL], tf[DEFER_UNROLL];
+    float sp[DEFER_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DEFER_UNROLL; ++u) {
+      const uint32_t e = e0 + 32 * u;
+      s0[u] = 0;
+      r[u] = make_uint4(0, 0, 0, 0);
+      if (e < cnt) {
+        r[u] = __ldg(a.rec + base + e);
+        s0[u] = __ldg(a.slot0 + base + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DEFER_UNROLL; ++u) {
+      const uint32_t p = s0[u] >> (a.kslot + 1);
+      tw[u] = __float_as_uint(__ldg(&a.table[p]).w);
+      tf[u] = __ldg(a.target_first + p);
+      sp[u] = __ldg(a.table_split + p);
+    }
+#pragma unroll
+    for (int u = 0; u < DEFER_UNROLL; ++u) {
+      if (e0 + 32 * u >= cnt) continue;
+      // child_of() with the final split word: the bin was refined (compare with the split position) unless
+      // every point of the node went left (:522-545: split word beyond the node's last bin)
+      const uint32_t q = 2 * tf[u] + 1;
+      uint32_t child = q >= tw[u] ? 1u : 0u;
+      if (q == tw[u]) child = !(__uint_as_float(r[u].y) < sp[u]) ? 1u : 0u;
+      const uint32_t slot = s0[u] + (child ? kbit : 0u);
+      static_cast<IDX *>(a.idx)[r[u].x] = (IDX)slot;
+      const long long w = WIN == WIN_CONST ? 1ll : (long long)(int)r[u].w;
+      atomicAdd(row_w + slot, (unsigned long long)w);
+      atomicMin(row_min + slot, f2key(__uint_as_float(r[u].z)));
+    }
+  }
+}
+
 // How many bins per node the next refinement pass uses: as many as fit `cap`
 // histogram slots for all `unresolved` nodes, at most 2^kmax.  The host runs the
 // same function on the count it reads back.
@@ -1451,6 +1695,7 @@ struct WalkArgs {
   float *table_next_split;   // per node: split position on this axis
   short *nshift_next;        // per child node: fixed-point shift (f64 weights)
   uint32_t *target;          // per node: idx value under refinement
+  uint32_t *target_first;    // per node: the same, kept after the node is decided (fix-up of the deferred points)
   const uint2 *node_rt;      // per node: {target, rank} of the refinement pass being walked
   float4 *rtable;            // per node: refinement bracket
   Trace trace;
@@ -1689,6 +1934,19 @@ __device__ void walk_node(const WalkArgs &a, unsigned char *smem_raw) {
     a.target[p] = (p << a.k0) + ns.sb;
     a.rtable[p] = make_float4(lo, hi, hi_incl ? 1.f : 0.f, 0.f);
     a.gp->any_undecided = 1;
+    if (a.first) {
+      // What the next level's dense sweep needs does not wait for the split: the children inherit this
+      // node's box on the next axis (:613-616 change the box on THIS axis only), and every point outside
+      // the one bin the bracket has shrunk to already knows its side.  The table entry singles that bin
+      // out (split word "refined inside bin target") and a NaN split position says "undecided": the sweep
+      // defers those points (rcb_kernels.cuh "Deferred points").
+      float inv, hme;
+      fast_bin_params(ns.box_lo[next_axis], ns.box_hi[next_axis], a.k_next, inv, hme);
+      a.table_next[p] = make_float4(ns.box_lo[next_axis], inv, hme, __uint_as_float(split_word(a.target[p], true)));
+      a.table_next_hi[p] = ns.box_hi[next_axis];
+      a.table_next_split[p] = __int_as_float(0x7FC00000);
+      a.target_first[p] = a.target[p];
+    }
     return;
   }
   ns.done = 1;

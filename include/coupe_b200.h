@@ -54,6 +54,9 @@ typedef struct coupe_b200_stats {
 	uint64_t refine_points;  /* points re-binned by the refinement sweeps (this rank) */
 	double   exchange_wait_ms; /* multi-GPU, peer-memory exchange: time the walks of this rank waited for the other
 	                              ranks' histograms (first block of every pass, SM cycles at the nominal clock) */
+	uint32_t deferred_levels;  /* levels left undecided by their dense pass whose refinement read the list of deferred
+	                              points written by the next level's dense sweep (no rescan of the idx words) */
+	uint32_t list_refine_sweeps; /* ... refinement passes over such a list (counted in refine_sweeps too) */
 } coupe_b200_stats;
 
 /* One context per process and GPU.  `device` is a CUDA ordinal.  Returns a

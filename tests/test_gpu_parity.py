@@ -492,6 +492,43 @@ def test_refinement_with_dense_matches(cb, oracle):
             ctx.close()
 
 
+@pytest.mark.parametrize("wk", ["i32", "i64", "const_i32", "const_f64_odd", "f64", "f64int"])
+@pytest.mark.parametrize("opts", [{}, {"kmax_a": 3, "kmax_refine": 3}, {"kmax_a": 2, "kmax_refine": 1},
+                                  {"kmax_a": 5, "kmax_refine": 10}])
+def test_deferred_refinement(cb, oracle, wk, opts):
+    """Levels left undecided by their dense pass: the next level's dense sweep lists the points of the undecided
+    bins, the refinement reads the list, the listed points then take their child (rcb_kernels.cuh "Deferred
+    points").  Same ids, same split tree as the oracle and as the idx-rescanning refinement (option defer=0)."""
+    rng = np.random.default_rng(sum(map(ord, wk)) + len(opts))
+    for pk, n, dim, iters, tol in [("cluster", 300_007, 3, 9, 0.001), ("grid", 200_000, 2, 7, 0.0),
+                                   ("negative", 150_001, 3, 8, 0.01)]:
+        pts = gen_points(rng, n, dim, pk)
+        if pk == "cluster":  # a tight cluster: most of a node inside the one bin under refinement
+            tight = rng.random(n) < 0.5
+            pts[tight] = pts[0] + rng.normal(size=(int(tight.sum()), dim)) * 1e-4
+        w = gen_weights(rng, n, wk)
+        want, tr = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
+        v = tr.visited.astype(bool)
+        seen = {}
+        for defer in (1, 0):
+            ctx = cb.Context(0)
+            ctx.set_option("defer", defer)
+            for k, val in opts.items():
+                ctx.set_option(k, val)
+            got = run_device(cb, pts, w, iters, tol, ctx=ctx)
+            assert np.array_equal(got, want), f"defer={defer}: {int((got != want).sum())} of {n} ids differ"
+            t = ctx.trace(iters)
+            assert np.array_equal(t["visited"], tr.visited)
+            assert np.array_equal(t["split_pos"][v], tr.split_pos[v])
+            assert np.array_equal(t["iters"][v], tr.iters[v])
+            assert np.array_equal(t["weight_left"][v], tr.weight_left[v])
+            seen[defer] = ctx.stats()
+            ctx.close()
+        assert seen[0]["deferred_levels"] == 0 and seen[0]["list_refine_sweeps"] == 0
+        if seen[0]["refine_sweeps"] > 1 or opts:  # (a refinement of the last level alone still scans)
+            assert seen[1]["deferred_levels"] > 0 and seen[1]["list_refine_sweeps"] > 0
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_rib_against_oracle(cb, oracle, dim):
     rng = np.random.default_rng(dim)

@@ -24,7 +24,11 @@ def _worker(rank, world, port, cases, out):
     try:
         ctx = cdist.init_comm(coupe_b200.Context(rank))
         results = []
-        for pts, w, iters, tol, rib, empty_last, peer in cases:
+        for case in cases:
+            pts, w, iters, tol, rib, empty_last, peer = case[:7]
+            opts = dict({"kmax_a": 8, "kmax_refine": 10}, **(case[7] if len(case) > 7 else {}))
+            for k, v in opts.items():
+                ctx.set_option(k, v)
             n = pts.shape[0]
             b, e = cdist.shard_range(n, rank, world)
             if rank == world - 1 and empty_last:  # last rank holds nothing
@@ -69,7 +73,7 @@ def run_sharded(cases, world=2):
         p.join(timeout=60)
     out = []
     for i, case in enumerate(cases):
-        assert all(r[1][i][1] == int(case[-1]) for r in res), "peer-memory exchange was requested but not used (or the reverse)"
+        assert all(r[1][i][1] == int(case[6]) for r in res), "peer-memory exchange was requested but not used (or the reverse)"
         assert all(r[1][i][2] == case[0].shape[0] for r in res)
         out.append(np.concatenate([r[1][i][0] for r in res]))
     return out
@@ -97,10 +101,16 @@ RCB_CASES = [
     ("f64lognormal", 3, 8, 0.02, False),  # wide form: per-node units, f64 weights re-read at every level
     ("f64negative", 2, 7, 0.05, True),    # ... with one global unit, found by the rank that holds the negative weight
     ("i32", 3, 11, 0.05, False),          # 2^11 parts: every level keeps block-private histograms (up to 12 levels)
+    # few candidates per pass: most levels stay undecided after their dense pass, the next level's sweep defers the
+    # points of the undecided bins on every rank and the refinement reads the lists (several passes per level)
+    ("i64", 3, 9, 0.001, False, {"kmax_a": 3, "kmax_refine": 3}),
+    ("f64", 3, 10, 0.01, True, {"kmax_a": 2, "kmax_refine": 2}),
+    ("const", 2, 8, 0.0, False, {"kmax_a": 4, "kmax_refine": 10}),
 ]
 
 
-def make_case(wkind, dim, iters, tol, empty_last, peer):
+def make_case(wkind, dim, iters, tol, empty_last, *rest):
+    peer, opts = rest[-1], (rest[0] if len(rest) > 1 else {})
     rng = np.random.default_rng(11)
     n = 300_007
     k = rng.integers(0, 5, n)
@@ -113,7 +123,7 @@ def make_case(wkind, dim, iters, tol, empty_last, peer):
          "f64lognormal": rng.lognormal(0.0, 5.0, n),
          "f64negative": np.where(np.arange(n) == n - 99_999, -0.125, rng.uniform(0.5, 1.5, n)),
          "const": np.array(3, dtype=np.int32)}[wkind]
-    return (pts, w, iters, tol, False, empty_last, peer)
+    return (pts, w, iters, tol, False, empty_last, peer, opts)
 
 
 @pytest.mark.parametrize("peer", [True, False], ids=["peer-exchange", "nccl"])
