@@ -34,6 +34,9 @@ COUPE_B200_TOOLS_H_SYMBOLS = ["coupe_b200_barycentres_device", "coupe_b200_weigh
                               "coupe_b200_imbalance_device", "coupe_b200_mewe_write", "coupe_b200_mewe_read",
                               "coupe_b200_mepe_write", "coupe_b200_mepe_read", "coupe_b200_free",
                               "coupe_b200_parse_rcb_spec"]
+# include/coupe_b200_mj.h
+COUPE_B200_MJ_H_SYMBOLS = ["coupe_b200_multi_jagged_device", "coupe_b200_multi_jagged_host",
+                           "coupe_b200_axis_sort_device", "coupe_b200_mj_scheme", "coupe_b200_mj_last_times"]
 
 
 class Stats(C.Structure):
@@ -166,6 +169,20 @@ def lib():
     L.coupe_b200_free.argtypes = [C.c_void_p]
     L.coupe_b200_parse_rcb_spec.restype = C.c_int
     L.coupe_b200_parse_rcb_spec.argtypes = [C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
+    # include/coupe_b200_mj.h
+    L.coupe_b200_multi_jagged_device.restype = C.c_int
+    L.coupe_b200_multi_jagged_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                 C.c_void_p, C.c_size_t, C.c_size_t]
+    L.coupe_b200_multi_jagged_host.restype = C.c_int
+    L.coupe_b200_multi_jagged_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.c_size_t]
+    L.coupe_b200_axis_sort_device.restype = C.c_int
+    L.coupe_b200_axis_sort_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                              C.c_size_t, C.c_size_t]
+    L.coupe_b200_mj_scheme.restype = C.c_int
+    L.coupe_b200_mj_scheme.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.coupe_b200_mj_last_times.restype = C.c_int
+    L.coupe_b200_mj_last_times.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

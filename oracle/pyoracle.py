@@ -35,7 +35,7 @@ class _Trace(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (g++)."""
-    srcs = [os.path.join(_HERE, f) for f in ("rcb_oracle.cpp", "tools_oracle.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("rcb_oracle.cpp", "tools_oracle.cpp", "mj_oracle.cpp")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-C", _HERE, "clean", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -292,3 +292,40 @@ def part_loads(num_parts, partition, weights):
     if err:
         raise IndexError("part id out of range")
     return loads
+
+
+# ---- Multi-Jagged and axis_sort (oracle/mj_oracle.cpp) ----
+
+def mj_axis_sort(points, permutation, coord):
+    """recursive_bisection.rs:815-827 with ties kept in their previous order; returns the sorted permutation."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    perm = np.array(permutation, dtype=np.uint64)
+    f = lib().mj_oracle_axis_sort
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64]
+    f(pts.ctypes.data, pts.shape[1], perm.ctypes.data, perm.size, coord)
+    return perm
+
+
+def mj_scheme(part_count, max_iter):
+    """(leaves, levels with a split) of multi_jagged.rs:70-98's partition scheme; None where the reference panics."""
+    f = lib().mj_oracle_scheme
+    f.restype = C.c_int64
+    f.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    depth = C.c_uint64(0)
+    leaves = f(part_count, max_iter, C.byref(depth))
+    return None if leaves < 0 else (int(leaves), int(depth.value))
+
+
+def multi_jagged(points, weights, part_count, max_iter, chunk=0):
+    """MultiJagged { part_count, max_iter } (multi_jagged.rs:150-179); None where the reference would panic.
+    chunk: elements per fold chunk of compute_split_positions (0: one chunk per node)."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    assert pts.ndim == 2 and pts.shape[1] in (2, 3) and w.shape == (pts.shape[0],)
+    part = np.zeros(pts.shape[0], dtype=np.uint64)
+    f = lib().mj_oracle_partition
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    rc = f(part.ctypes.data, pts.shape[1], pts.shape[0], pts.ctypes.data, w.ctypes.data, part_count, max_iter, chunk)
+    return None if rc else part

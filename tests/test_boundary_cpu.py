@@ -26,9 +26,10 @@ def declared(header):
 
 def test_every_declared_symbol_is_exported(lib):
     L = lib.lib()
-    names = declared("coupe.h") + declared("coupe_b200.h")
+    names = declared("coupe.h") + declared("coupe_b200.h") + declared("coupe_b200_mj.h")
     assert set(lib.COUPE_H_SYMBOLS) == set(declared("coupe.h"))
     assert set(lib.COUPE_B200_H_SYMBOLS) == set(declared("coupe_b200.h"))
+    assert set(lib.COUPE_B200_MJ_H_SYMBOLS) == set(declared("coupe_b200_mj.h"))
     for name in names:
         assert getattr(L, name) is not None
 
