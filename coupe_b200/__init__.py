@@ -5,7 +5,7 @@ from .api import (BackendError, Context, Error, Group, InputLenMismatch, Rcb, Ri
                   default_context)
 from . import _lib  # noqa: F401
 from . import tools  # noqa: F401
-from .multi_jagged import MultiJagged, axis_sort  # noqa: F401
+from .multi_jagged import Grid, MultiJagged, axis_sort  # noqa: F401
 
 __all__ = ["Rcb", "Rib", "Context", "Group", "Error", "InputLenMismatch", "BackendError", "default_context", "tools",
-           "MultiJagged", "axis_sort"]
+           "MultiJagged", "axis_sort", "Grid"]

@@ -36,7 +36,8 @@ COUPE_B200_TOOLS_H_SYMBOLS = ["coupe_b200_barycentres_device", "coupe_b200_weigh
                               "coupe_b200_parse_rcb_spec"]
 # include/coupe_b200_mj.h
 COUPE_B200_MJ_H_SYMBOLS = ["coupe_b200_multi_jagged_device", "coupe_b200_multi_jagged_host",
-                           "coupe_b200_axis_sort_device", "coupe_b200_mj_scheme", "coupe_b200_mj_last_times"]
+                           "coupe_b200_axis_sort_device", "coupe_b200_mj_scheme", "coupe_b200_mj_last_times",
+                           "coupe_b200_grid_rcb_device", "coupe_b200_grid_rcb_host"]
 
 
 class Stats(C.Structure):
@@ -183,6 +184,12 @@ def lib():
     L.coupe_b200_mj_scheme.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.coupe_b200_mj_last_times.restype = C.c_int
     L.coupe_b200_mj_last_times.argtypes = [C.c_void_p, C.c_void_p]
+    L.coupe_b200_grid_rcb_device.restype = C.c_int
+    L.coupe_b200_grid_rcb_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_size_t, C.c_size_t]
+    L.coupe_b200_grid_rcb_host.restype = C.c_int
+    L.coupe_b200_grid_rcb_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_size_t, C.c_size_t]
     _lib = L
     return L
 

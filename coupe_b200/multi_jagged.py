@@ -84,3 +84,48 @@ def axis_sort(points, permutation, coord: int, context: "Context | None" = None)
                                                      int(permutation.shape[0]), int(coord))
     if err != 0:
         raise BackendError(err)
+
+
+@dataclass
+class Grid:
+    """coupe::Grid (coupe/src/cartesian/mod.rs:44-47): `Grid(width, height)` is new_2d, `Grid(width, height, depth)`
+    new_3d.  `rcb(partition, weights, iter_count)` is Grid::rcb (mod.rs:119-181): weights and part ids are row major,
+    one per cell; i64 or f64 weights.  `threads` is the size of the rayon pool the reference would run under (its
+    weighted median chunks the search range by it, rcb.rs:64-68, so the result depends on it); default: the host's
+    logical CPUs like rayon's global pool, at least 2."""
+
+    width: int
+    height: int
+    depth: "int | None" = None
+    context: "Context | None" = None
+
+    def rcb(self, partition, weights, iter_count: int, threads: "int | None" = None):
+        import os
+
+        sizes = [self.width, self.height] + ([self.depth] if self.depth is not None else [])
+        cells = int(np.prod(sizes))
+        if int(weights.shape[0]) != cells:
+            raise InputLenMismatch(cells, int(weights.shape[0]))
+        if int(partition.shape[0]) != cells:
+            raise InputLenMismatch(cells, int(partition.shape[0]))
+        threads = int(threads) if threads is not None else max(2, os.cpu_count() or 2)
+        sz = (C.c_uint64 * 3)(*(sizes + [1] * (3 - len(sizes))))
+        L = _lib.lib()
+        if _is_torch(weights):
+            import torch
+
+            ctx = self.context or default_context(weights.device.index)
+            wtype = {torch.int64: _lib.COUPE_INT64, torch.float64: _lib.COUPE_DOUBLE}[weights.dtype]
+            assert weights.is_contiguous() and partition.is_contiguous() and partition.dtype in (torch.int64, torch.uint64)
+            with torch.cuda.device(weights.device):
+                err = L.coupe_b200_grid_rcb_device(ctx._h, torch.cuda.current_stream().cuda_stream, partition.data_ptr(),
+                                                   len(sizes), sz, wtype, weights.data_ptr(), int(iter_count), threads)
+        else:
+            ctx = self.context or default_context(0)
+            w = np.ascontiguousarray(weights)
+            wtype = {np.dtype(np.int64): _lib.COUPE_INT64, np.dtype(np.float64): _lib.COUPE_DOUBLE}[w.dtype]
+            assert partition.dtype == np.uint64 and partition.flags.c_contiguous
+            err = L.coupe_b200_grid_rcb_host(ctx._h, partition.ctypes.data, len(sizes), sz, wtype, w.ctypes.data,
+                                             int(iter_count), threads)
+        if err != 0:
+            raise BackendError(err)

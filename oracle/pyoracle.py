@@ -35,7 +35,7 @@ class _Trace(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (g++)."""
-    srcs = [os.path.join(_HERE, f) for f in ("rcb_oracle.cpp", "tools_oracle.cpp", "mj_oracle.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("rcb_oracle.cpp", "tools_oracle.cpp", "mj_oracle.cpp", "grid_oracle.cpp")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-C", _HERE, "clean", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -329,3 +329,32 @@ def multi_jagged(points, weights, part_count, max_iter, chunk=0):
     f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
     rc = f(part.ctypes.data, pts.shape[1], pts.shape[0], pts.ctypes.data, w.ctypes.data, part_count, max_iter, chunk)
     return None if rc else part
+
+
+# ---- cartesian RCB, Grid::rcb (oracle/grid_oracle.cpp) ----
+
+def grid_rcb(sizes, weights, iter_count, threads):
+    """Grid::new_2d/new_3d(sizes).rcb(partition, weights, iter_count) under a rayon pool of `threads` threads
+    (coupe/src/cartesian/mod.rs:119-181).  weights: i64 or f64, row major; returns the partition (uint64)."""
+    w = np.ascontiguousarray(weights)
+    wtype = {np.dtype(np.int64): 1, np.dtype(np.float64): 2}[w.dtype]
+    sz = np.array(list(sizes), dtype=np.uint64)
+    assert w.size == int(np.prod(sz))
+    part = np.zeros(w.size, dtype=np.uint64)
+    f = lib().grid_oracle_rcb
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64]
+    rc = f(part.ctypes.data, len(sz), sz.ctypes.data, wtype, w.ctypes.data, iter_count, threads)
+    return None if rc else part
+
+
+def grid_weighted_median(weights, threads):
+    """weighted_median (coupe/src/cartesian/rcb.rs:52-99): (position, left_weight)."""
+    w = np.ascontiguousarray(weights)
+    wtype = {np.dtype(np.int64): 1, np.dtype(np.float64): 2}[w.dtype]
+    f = lib().grid_oracle_weighted_median
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    pos, lw = C.c_uint64(0), C.c_double(0)
+    rc = f(wtype, w.ctypes.data, w.size, threads, C.byref(pos), C.byref(lw))
+    return None if rc else (int(pos.value), float(lw.value))
