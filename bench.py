@@ -589,6 +589,8 @@ def run_ours(args):
     sweeps = []  # (ms, level, kind) of the timed steps
     refine_n = 0
     refine_pts = 0
+    deferred_n = 0
+    list_n = 0
     xwait = 0.0
     stats_last = None
     e0 = torch.cuda.Event(enable_timing=True)
@@ -607,6 +609,8 @@ def run_ours(args):
             sweeps += ctx.sweep_times()
         refine_n += st["refine_sweeps"]
         refine_pts += st["refine_points"]
+        deferred_n += st["deferred_levels"]
+        list_n += st["list_refine_sweeps"]
         xwait += st["exchange_wait_ms"]
         stats_last = st
     e1.record()
@@ -758,6 +762,8 @@ def run_ours(args):
         "config": config,
         "run": {"points_per_gpu": n, "refine_sweeps_per_step": refine_n / args.steps,
                 "refine_points_per_step": refine_pts / args.steps,
+                "deferred_levels_per_step": deferred_n / args.steps,
+                "refine_sweeps_over_lists_per_step": list_n / args.steps,
                 "f64_weight_form": None if cfg["weights"] not in ("f64", "linear") else ("wide" if wide else "narrow"),
                 "peer_exchange": int(stats_last["peer_exchange"]) if stats_last else None,
                 "collectives_per_step": int(stats_last["collectives"]) if stats_last else None,

@@ -151,52 +151,65 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *hist, size_t
   }
 }
 
-// stable scatter of one tile: the tile is read in order, SORT_THREADS elements at a time; an element's place is
-// (tile offset of its digit) + (elements of that digit seen before it in the tile)
+// Stable scatter of one tile.  Warp w owns the w-th run of 32 * SORT_ITEMS consecutive elements of the tile
+// and keeps them in registers: (1) every warp counts the digits of its run, (2) one scan per digit over the
+// warps in order, from the tile's global offset of that digit, gives every warp its first place per digit,
+// (3) every warp places its elements round by round, in order.  Two block barriers per tile; an element's
+// place is (tile offset of its digit) + (elements of that digit in front of it in the tile).
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(size_t n, const unsigned long long *__restrict__ key_in, const unsigned long long *__restrict__ pay_in,
                      unsigned long long *__restrict__ key_out, unsigned long long *__restrict__ pay_out, int pass,
                      const uint32_t *__restrict__ offs) {
-  __shared__ uint32_t s_base[RADIX];               // next free place of every digit
-  __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];    // per warp: elements of the digit in this round, then their base
-  s_base[threadIdx.x] = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+  __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];  // per warp: elements of the digit in its run, then its next free place
+  for (int w = 0; w < SORT_WARPS; ++w) s_cnt[w][threadIdx.x] = 0;
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t tile = (size_t)SORT_THREADS * SORT_ITEMS, lo = blockIdx.x * tile, hi = min(n, lo + tile);
-  for (size_t r = lo; r < hi; r += SORT_THREADS) {
-    for (int w = 0; w < SORT_WARPS; ++w) s_cnt[w][threadIdx.x] = 0;
-    __syncthreads();
-    const size_t j = r + threadIdx.x;
+  const size_t run0 = lo + (size_t)warp * 32 * SORT_ITEMS;
+  unsigned long long k[SORT_ITEMS], p[SORT_ITEMS];
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    const size_t j = run0 + (size_t)r * 32 + lane;
     const bool valid = j < hi;
-    unsigned long long k = 0, p = 0;
-    uint32_t d = 0, rank = 0;
+    k[r] = 0;
+    p[r] = 0;
     if (valid) {
-      k = key_in[j];
-      p = pay_in[j];
-      d = digit_of(k, p, pass);
+      k[r] = key_in[j];
+      p[r] = pay_in[j];
     }
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
     if (valid) {
+      const uint32_t d = digit_of(k[r], p[r], pass);
       const uint32_t peers = __match_any_sync(vmask, d);
-      rank = __popc(peers & ((1u << lane) - 1));
-      if (rank == 0) s_cnt[warp][d] = __popc(peers);  // one writer per (warp, digit)
+      if ((int)lane == __ffs(peers) - 1) s_cnt[warp][d] += __popc(peers);  // one writer per digit and round
     }
-    __syncthreads();
-    {  // thread = digit: places of the warps in warp order, then the digit's running base moves on
-      uint32_t run = s_base[threadIdx.x];
-      for (int w = 0; w < SORT_WARPS; ++w) {
-        const uint32_t c = s_cnt[w][threadIdx.x];
-        s_cnt[w][threadIdx.x] = run;
-        run += c;
-      }
-      s_base[threadIdx.x] = run;
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread = digit: the warps' first places, in warp order
+    uint32_t run = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      const uint32_t c = s_cnt[w][threadIdx.x];
+      s_cnt[w][threadIdx.x] = run;
+      run += c;
     }
-    __syncthreads();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    const size_t j = run0 + (size_t)r * 32 + lane;
+    const bool valid = j < hi;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
     if (valid) {
-      const uint32_t dst = s_cnt[warp][d] + rank;
-      key_out[dst] = k;
-      pay_out[dst] = p;
+      const uint32_t d = digit_of(k[r], p[r], pass);
+      const uint32_t peers = __match_any_sync(vmask, d);
+      const uint32_t dst = s_cnt[warp][d] + __popc(peers & ((1u << lane) - 1));
+      key_out[dst] = k[r];
+      pay_out[dst] = p[r];
+      __syncwarp(vmask);  // every peer has read the place before its first lane moves it on
+      if ((int)lane == __ffs(peers) - 1) s_cnt[warp][d] += __popc(peers);
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 

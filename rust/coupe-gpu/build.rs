@@ -26,6 +26,8 @@ fn main() {
             .arg(csrc.join("engine.cu"))
             .arg(csrc.join("ffi.cu"))
             .arg(csrc.join("tools.cu"))
+            .arg(csrc.join("mj.cu"))
+            .arg(csrc.join("grid.cu"))
             .args(["-ldl", "-lpthread"])
             .status()
             .expect("nvcc not found: set NVCC or enable the `prebuilt` feature");
@@ -35,7 +37,7 @@ fn main() {
         println!("cargo:rustc-link-search=native={}", root.join("coupe_b200/lib").display());
     }
     println!("cargo:rustc-link-lib=dylib=coupe_b200");
-    for f in ["engine.cu", "ffi.cu", "tools.cu", "rcb_kernels.cuh"] {
+    for f in ["engine.cu", "ffi.cu", "tools.cu", "mj.cu", "grid.cu", "rcb_kernels.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/coupe_b200.h").display());

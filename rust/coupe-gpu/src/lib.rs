@@ -16,6 +16,7 @@ use std::os::raw::{c_char, c_int};
 
 use coupe::{Partition, PointND};
 
+pub mod mj;
 pub mod tools;
 
 #[repr(C)]
@@ -57,6 +58,17 @@ pub enum GpuError {
     Backend { code: i32, message: String },
 }
 
+impl GpuError {
+    /// `Ok(())` for COUPE_ERR_OK, the backend error otherwise.
+    pub(crate) fn check(code: c_int) -> Result<(), GpuError> {
+        if code == 0 {
+            Ok(())
+        } else {
+            Err(backend(code))
+        }
+    }
+}
+
 fn backend(code: c_int) -> GpuError {
     let message = unsafe { std::ffi::CStr::from_ptr(coupe_strerror(code)) }
         .to_string_lossy()
@@ -80,7 +92,7 @@ impl GpuWeight for f64 {
 }
 
 /// One context per process and GPU (scratch buffers are kept between calls).
-pub struct Context(*mut Ctx);
+pub struct Context(pub(crate) *mut Ctx);
 unsafe impl Send for Context {}
 
 impl Context {
