@@ -19,9 +19,9 @@ done
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02b_bench_reference_n1.json 2> gpurun_out/bench_ref.err; cat gpurun_out/r02b_bench_reference_n1.json | cut -c1-600
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --parity off --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
 QB="python tools/quick_bench.py --n 125000000 --w f64 --dist gauss --reps 0"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -c 10 -o gpurun_out/prof_sweeps -f $QB > gpurun_out/prof1.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:sweep_kernel -c 10 -o gpurun_out/prof_sweeps -f $QB > gpurun_out/prof1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"defer_|sweep_refine" -c 3 -o gpurun_out/prof_defer -f $QB > gpurun_out/prof2.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"radix_|mj_" -c 40 -o gpurun_out/prof_mj -f python - > gpurun_out/prof3.log 2>&1 <<'PY'
+timeout 600 ncu --set full --clock-control none -k regex:"radix_|mj_" -s 3 -c 9 -o gpurun_out/prof_mj -f python - > gpurun_out/prof3.log 2>&1 <<'PY'
 import torch, coupe_b200
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(1)
@@ -31,4 +31,4 @@ w = torch.rand(n, dtype=torch.float64, device=dev, generator=g) + 0.5
 part = torch.empty(n, dtype=torch.int64, device=dev)
 coupe_b200.MultiJagged(512, 3).partition(part, (pts, w))
 PY
-ls -la gpurun_out/*.ncu-rep
+ls -la gpurun_out/*.ncu-rep; du -sm gpurun_out
