@@ -129,26 +129,44 @@ radix_hist_kernel(size_t n, const unsigned long long *__restrict__ key, const un
   hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-// exclusive scan of hist in (digit, tile) order, one block; `total` entries
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *hist, size_t total) {
-  __shared__ uint32_t s_part[1024];
-  const size_t per = (total + 1023) / 1024, lo = min(total, threadIdx.x * per), hi = min(total, lo + per);
+// Offsets of every (digit, tile) pair = exclusive scan of hist in (digit, tile) order, in two steps: block d scans
+// row d (the tiles of digit d) in place and leaves the row's total; one small block then scans the 256 totals into
+// the digits' first places (`base`), which the scatter adds.  (One block over all 256 x tiles entries took 570 us
+// per pass at 10^7 elements, more than the scatter itself.)
+__global__ void __launch_bounds__(SORT_THREADS) radix_scan_rows_kernel(uint32_t *hist, uint32_t tiles, uint32_t *totals) {
+  __shared__ uint32_t s_part[SORT_THREADS];
+  uint32_t *row = hist + (size_t)blockIdx.x * tiles;
+  const uint32_t per = (tiles + SORT_THREADS - 1) / SORT_THREADS;
+  const uint32_t lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
   uint32_t acc = 0;
-  for (size_t i = lo; i < hi; ++i) acc += hist[i];
+  for (uint32_t i = lo; i < hi; ++i) acc += row[i];
   s_part[threadIdx.x] = acc;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan of the partials
+  for (int d = 1; d < SORT_THREADS; d <<= 1) {  // inclusive scan of the partials
     const uint32_t v = threadIdx.x >= (unsigned)d ? s_part[threadIdx.x - d] : 0u;
     __syncthreads();
     s_part[threadIdx.x] += v;
     __syncthreads();
   }
   uint32_t run = threadIdx.x ? s_part[threadIdx.x - 1] : 0u;
-  for (size_t i = lo; i < hi; ++i) {
-    const uint32_t v = hist[i];
-    hist[i] = run;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t v = row[i];
+    row[i] = run;
     run += v;
   }
+  if (threadIdx.x == SORT_THREADS - 1) totals[blockIdx.x] = s_part[SORT_THREADS - 1];
+}
+__global__ void __launch_bounds__(RADIX) radix_scan_digits_kernel(const uint32_t *totals, uint32_t *base) {
+  __shared__ uint32_t s[RADIX];
+  s[threadIdx.x] = totals[threadIdx.x];
+  __syncthreads();
+  for (int d = 1; d < RADIX; d <<= 1) {
+    const uint32_t v = threadIdx.x >= (unsigned)d ? s[threadIdx.x - d] : 0u;
+    __syncthreads();
+    s[threadIdx.x] += v;
+    __syncthreads();
+  }
+  base[threadIdx.x] = threadIdx.x ? s[threadIdx.x - 1] : 0u;
 }
 
 // Stable scatter of one tile.  Warp w owns the w-th run of 32 * SORT_ITEMS consecutive elements of the tile
@@ -159,7 +177,7 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *hist, size_t
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(size_t n, const unsigned long long *__restrict__ key_in, const unsigned long long *__restrict__ pay_in,
                      unsigned long long *__restrict__ key_out, unsigned long long *__restrict__ pay_out, int pass,
-                     const uint32_t *__restrict__ offs) {
+                     const uint32_t *__restrict__ offs, const uint32_t *__restrict__ base) {
   __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];  // per warp: elements of the digit in its run, then its next free place
   for (int w = 0; w < SORT_WARPS; ++w) s_cnt[w][threadIdx.x] = 0;
   __syncthreads();
@@ -187,7 +205,7 @@ radix_scatter_kernel(size_t n, const unsigned long long *__restrict__ key_in, co
   }
   __syncthreads();
   {  // thread = digit: the warps' first places, in warp order
-    uint32_t run = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    uint32_t run = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x] + base[threadIdx.x];
     for (int w = 0; w < SORT_WARPS; ++w) {
       const uint32_t c = s_cnt[w][threadIdx.x];
       s_cnt[w][threadIdx.x] = run;
@@ -415,9 +433,11 @@ void radix_sort(cudaStream_t st, size_t n, unsigned long long *&ka, unsigned lon
   const unsigned tiles = (unsigned)((n + tile - 1) / tile);
   if (!tiles) return;
   for (int pass : passes) {
+    uint32_t *totals = hist + (size_t)RADIX * tiles, *base = totals + RADIX;
     radix_hist_kernel<<<tiles, SORT_THREADS, 0, st>>>(n, ka, pa, pass, hist);
-    radix_scan_kernel<<<1, 1024, 0, st>>>(hist, (size_t)RADIX * tiles);
-    radix_scatter_kernel<<<tiles, SORT_THREADS, 0, st>>>(n, ka, pa, kb, pb, pass, hist);
+    radix_scan_rows_kernel<<<RADIX, SORT_THREADS, 0, st>>>(hist, tiles, totals);
+    radix_scan_digits_kernel<<<1, RADIX, 0, st>>>(totals, base);
+    radix_scatter_kernel<<<tiles, SORT_THREADS, 0, st>>>(n, ka, pa, kb, pb, pass, hist, base);
     std::swap(ka, kb);
     std::swap(pa, pb);
   }
@@ -469,7 +489,7 @@ int mj_run(int device, cudaStream_t st, uint64_t *part_dev, int D, size_t n, con
   S.key_b.ensure(n * 8);
   S.pay_a.ensure(n * 8);
   S.pay_b.ensure(n * 8);
-  S.hist.ensure((size_t)RADIX * tiles * 4);
+  S.hist.ensure(((size_t)RADIX * tiles + 2 * RADIX) * 4);
   const size_t max_chunks = n / CHUNK + final_entries + 2;
   S.csum.ensure(max_chunks * 8);
   S.ws.ensure(n * 8);
@@ -653,7 +673,7 @@ int coupe_b200_axis_sort_device(coupe_b200_ctx *ctx, void *stream, uintptr_t dim
     S.key_b.ensure(len * 8);
     S.pay_a.ensure(len * 8);
     S.pay_b.ensure(len * 8);
-    S.hist.ensure((size_t)RADIX * tiles * 4);
+    S.hist.ensure(((size_t)RADIX * tiles + 2 * RADIX) * 4);
     unsigned long long *ka = S.key_a.as<unsigned long long>(), *kb = S.key_b.as<unsigned long long>();
     unsigned long long *pa = S.pay_a.as<unsigned long long>(), *pb = S.pay_b.as<unsigned long long>();
     mj_axis_keys_kernel<<<grid_for(len, 256), 256, 0, st>>>(len, (int)dim, (int)coord, points_dev,
