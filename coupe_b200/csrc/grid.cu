@@ -71,23 +71,63 @@ struct Wt<long long> {
   __device__ static long long store(long long v) { return v; }
 };
 
+// Rows are contiguous in memory and must be added left to right (the reference's order, bit for bit in f64): a
+// warp takes 32 rows at a time, loads a 32 x 32 tile with every load coalesced along x, and lane r then adds the
+// 32 values of row r in order from shared memory.
+constexpr int TILE_WARPS = 4;
+constexpr int TILE_ROWS = 8, TILE_COLS = 128;  // per warp and step: 8 rows x 128 columns (32 loads in flight per lane);
+                                               // 8 rows per warp rather than 32: four times as many warps for the same rows
 // every row (cells consecutive along x) added left to right
 template <class W>
-__global__ void grid_rowsum_kernel(const W *__restrict__ w, unsigned long long width, unsigned long long rows,
-                                   W *__restrict__ rowsum) {
-  const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  W s = 0;
-  for (unsigned long long x = 0; x < width; ++x) s = Wt<W>::add(s, w[r * width + x]);
-  rowsum[r] = s;
+__global__ void __launch_bounds__(32 * TILE_WARPS)
+grid_rowsum_kernel(const W *__restrict__ w, unsigned long long width, unsigned long long rows, W *__restrict__ rowsum) {
+  __shared__ W tile[TILE_WARPS][TILE_ROWS][TILE_COLS + 1];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned long long r0 = ((unsigned long long)blockIdx.x * TILE_WARPS + warp) * TILE_ROWS; r0 < rows;
+       r0 += (unsigned long long)gridDim.x * TILE_WARPS * TILE_ROWS) {
+    const unsigned rows_here = (unsigned)min((unsigned long long)TILE_ROWS, rows - r0);
+    W s = 0;
+    for (unsigned long long xb = 0; xb < width; xb += TILE_COLS) {
+      const unsigned cols = (unsigned)min((unsigned long long)TILE_COLS, width - xb);
+      W v[TILE_ROWS][TILE_COLS / 32];  // all the loads of the tile are issued before the first one is used (a store right
+                                       // after its load would wait for it: one memory latency per load, in turn)
+#pragma unroll
+      for (int r = 0; r < TILE_ROWS; ++r)
+#pragma unroll
+        for (int q = 0; q < TILE_COLS / 32; ++q)
+          v[r][q] = ((unsigned)r < rows_here && 32 * q + lane < cols) ? w[(r0 + r) * width + xb + 32 * q + lane] : (W)0;
+#pragma unroll
+      for (int r = 0; r < TILE_ROWS; ++r)
+#pragma unroll
+        for (int q = 0; q < TILE_COLS / 32; ++q) tile[warp][r][32 * q + lane] = v[r][q];
+      __syncwarp();
+      if (lane < rows_here)
+        for (unsigned c = 0; c < cols; ++c) s = Wt<W>::add(s, tile[warp][lane][c]);
+      __syncwarp();
+    }
+    if (lane < rows_here) rowsum[r0 + lane] = s;
+  }
 }
 
 template <class W>
 __global__ void grid_root_kernel(const W *__restrict__ rowsum, unsigned long long rows, GNode *nodes,
                                  unsigned long long sx, unsigned long long sy, unsigned long long sz) {
-  if (blockIdx.x || threadIdx.x) return;
+  if (blockIdx.x) return;
+  // the row sums are added in order (one chain of additions), fed by coalesced loads of 4 x 32 values at a time
+  const unsigned lane = threadIdx.x & 31;
   W t = 0;
-  for (unsigned long long r = 0; r < rows; ++r) t = Wt<W>::add(t, rowsum[r]);
+  for (unsigned long long r0 = 0; r0 < rows; r0 += 128) {
+    W v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = r0 + 32 * u + lane < rows ? rowsum[r0 + 32 * u + lane] : (W)0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      for (int j = 0; j < 32; ++j) {
+        const W x = Wt<W>::load(__shfl_sync(0xffffffffu, Wt<W>::store(v[u]), j));
+        if (r0 + 32 * u + j < rows) t = Wt<W>::add(t, x);
+      }
+  }
+  if (lane) return;
   GNode n{};
   n.size[0] = sx;
   n.size[1] = sy;
@@ -106,19 +146,70 @@ __global__ void grid_axis_kernel(const W *__restrict__ w, const GNode *__restric
   const GNode &nd = level_nodes[blockIdx.x];
   if (!nd.exists || nd.size[coord] == 0 || iters_left == 0) return;
   const int outer = D == 2 ? 1 - coord : (coord + 1) % 3, inner = D == 2 ? -1 : (coord + 2) % 3;
+  if (coord == 1) {
+    // the innermost loop of the reference runs along x (2-D: sum over x; 3-D: z outside, x inside): rows of the
+    // box, contiguous in memory, added left to right -> 32 x 32 tiles through shared memory, loads coalesced along x
+    __shared__ W tile[TILE_WARPS][TILE_ROWS][TILE_COLS + 1];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long nz = D == 2 ? 1 : nd.size[2], x0 = nd.offset[0], x1 = nd.offset[0] + nd.size[0];
+    for (unsigned long long a0 = ((unsigned long long)blockIdx.y * TILE_WARPS + warp) * TILE_ROWS; a0 < nd.size[1];
+         a0 += (unsigned long long)gridDim.y * TILE_WARPS * TILE_ROWS) {
+      const unsigned rows_here = (unsigned)min((unsigned long long)TILE_ROWS, nd.size[1] - a0);
+      W s = 0;
+      for (unsigned long long zi = 0; zi < nz; ++zi) {
+        const unsigned long long z = D == 2 ? 0 : nd.offset[2] + zi;
+        for (unsigned long long xb = x0; xb < x1; xb += TILE_COLS) {
+          const unsigned cols = (unsigned)min((unsigned long long)TILE_COLS, x1 - xb);
+          const unsigned long long row0 = nd.offset[1] + a0 + gy * z;
+          W v[TILE_ROWS][TILE_COLS / 32];  // (loads first, stores after: see grid_rowsum_kernel)
+#pragma unroll
+          for (int r = 0; r < TILE_ROWS; ++r)
+#pragma unroll
+            for (int q = 0; q < TILE_COLS / 32; ++q)
+              v[r][q] = ((unsigned)r < rows_here && 32 * q + lane < cols) ? w[xb + 32 * q + lane + gx * (row0 + r)] : (W)0;
+#pragma unroll
+          for (int r = 0; r < TILE_ROWS; ++r)
+#pragma unroll
+            for (int q = 0; q < TILE_COLS / 32; ++q) tile[warp][r][32 * q + lane] = v[r][q];
+          __syncwarp();
+          if (lane < rows_here)
+            for (unsigned c = 0; c < cols; ++c) s = Wt<W>::add(s, tile[warp][lane][c]);
+          __syncwarp();
+        }
+      }
+      if (lane < rows_here) axis[(unsigned long long)blockIdx.x * side + a0 + lane] = s;
+    }
+    return;
+  }
   for (unsigned long long a = (unsigned long long)blockIdx.y * blockDim.x + threadIdx.x; a < nd.size[coord];
        a += (unsigned long long)gridDim.y * blockDim.x) {
     unsigned long long pos[3] = {0, 0, 0};
     pos[coord] = nd.offset[coord] + a;
     W s = 0;
-    for (unsigned long long o = 0; o < nd.size[outer]; ++o) {
-      pos[outer] = nd.offset[outer] + o;
-      if (inner < 0) {
-        s = Wt<W>::add(s, w[pos[0] + gx * pos[1]]);
-      } else {
-        for (unsigned long long i = 0; i < nd.size[inner]; ++i) {
-          pos[inner] = nd.offset[inner] + i;
-          s = Wt<W>::add(s, w[pos[0] + gx * (pos[1] + gy * pos[2])]);
+    // strides of the two loops in cells; the values of 16 steps are loaded before they are added (in order)
+    const unsigned long long st[3] = {1ull, gx, gx * gy};
+    if (inner < 0) {
+      const W *p = w + pos[0] * st[0] + pos[1] * st[1] + nd.offset[outer] * st[outer];
+      for (unsigned long long o = 0; o < nd.size[outer]; o += 16) {
+        W v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = o + u < nd.size[outer] ? p[(o + u) * st[outer]] : (W)0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (o + u < nd.size[outer]) s = Wt<W>::add(s, v[u]);
+      }
+    } else {
+      for (unsigned long long o = 0; o < nd.size[outer]; ++o) {
+        pos[outer] = nd.offset[outer] + o;
+        pos[inner] = nd.offset[inner];
+        const W *p = w + pos[0] + gx * (pos[1] + gy * pos[2]);
+        for (unsigned long long i = 0; i < nd.size[inner]; i += 16) {
+          W v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = i + u < nd.size[inner] ? p[(i + u) * st[inner]] : (W)0;
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            if (i + u < nd.size[inner]) s = Wt<W>::add(s, v[u]);
         }
       }
     }
@@ -126,20 +217,26 @@ __global__ void grid_axis_kernel(const W *__restrict__ w, const GNode *__restric
   }
 }
 
-// weighted_median (rcb.rs:52-99) under a pool of `threads` threads, then the two children (:143-176)
+// weighted_median (rcb.rs:52-99) under a pool of `threads` threads, then the two children (:143-176).
+// One WARP per box: the chunks of a round (`fold_chunks`, :64-68) are summed by the lanes, one chunk each, every
+// chunk left to right from zero like the reference; the scan over the chunk sums (:69-90) is then replayed by all
+// lanes alike (uniform control flow, the sums fetched by shuffle).  Same chunks, same order of additions: bit-identical
+// results, with range / threads additions in sequence per round instead of range.
 template <class W>
-__global__ void grid_median_kernel(GNode *level_nodes, GNode *next_nodes, unsigned nodes, int coord, int D,
-                                   unsigned long long side, int iters_left, unsigned long long threads,
-                                   const W *__restrict__ axis_all, unsigned *err) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+grid_median_kernel(GNode *level_nodes, GNode *next_nodes, unsigned nodes, int coord, int D, unsigned long long side,
+                   int iters_left, unsigned long long threads, const W *__restrict__ axis_all, unsigned *err) {
+  const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= nodes) return;
   GNode &nd = level_nodes[i];
   GNode lo{}, hi{};
   if (!nd.exists || nd.size[coord] == 0 || iters_left == 0) {  // Whole (:110-112), or no such box
-    nd.split = 0;
-    if (next_nodes) {
-      next_nodes[2 * i] = lo;
-      next_nodes[2 * i + 1] = hi;
+    if (lane == 0) {
+      nd.split = 0;
+      if (next_nodes) {
+        next_nodes[2 * i] = lo;
+        next_nodes[2 * i + 1] = hi;
+      }
     }
     return;
   }
@@ -154,29 +251,37 @@ __global__ void grid_median_kernel(GNode *level_nodes, GNode *next_nodes, unsign
   int rounds = 0;
   while (!found) {
     if (++rounds > 256) {  // the range shrinks by a constant factor per round; NaN weights can stall the reference too
-      *err = 1;
+      if (lane == 0) *err = 1;
       position = mn;
       break;
     }
-    const unsigned long long chunk = max(1ull, (mx - mn) / threads), lo_i = mn;
+    const unsigned long long chunk = max(1ull, (mx - mn) / threads), lo_i = mn, hi_i = mx;
     const W left0 = left_weight;
     W prefix = 0;
-    for (unsigned long long start = lo_i; start < mx; start += chunk) {
-      const W pcw = Wt<W>::add(left0, prefix);  // weight in front of this chunk
+    bool stop = false;  // the reference's `break` out of the scan (:84-86)
+    for (unsigned long long c0 = lo_i; c0 < hi_i && !found && !stop; c0 += 32 * chunk) {
+      const unsigned long long mine = c0 + lane * chunk;
       W cw = 0;
-      for (unsigned long long k = start; k < min(start + chunk, mx); ++k) cw = Wt<W>::add(cw, weights[k]);
-      prefix = Wt<W>::add(prefix, cw);
-      if (pcw < min_part) {
-        mn = start;
-        left_weight = pcw;
-      } else if (max_part < pcw) {
-        mx = start;
-        break;
-      } else {
-        position = start;
-        left_weight = pcw;
-        found = true;
-        break;
+      for (unsigned long long k = mine; k < min(mine + chunk, hi_i); ++k) cw = Wt<W>::add(cw, weights[k]);
+      for (int j = 0; j < 32; ++j) {
+        const unsigned long long start = c0 + j * chunk;
+        if (start >= hi_i) break;
+        const W cwj = Wt<W>::load(__shfl_sync(0xffffffffu, Wt<W>::store(cw), j));
+        const W pcw = Wt<W>::add(left0, prefix);  // weight in front of this chunk
+        prefix = Wt<W>::add(prefix, cwj);
+        if (pcw < min_part) {
+          mn = start;
+          left_weight = pcw;
+        } else if (max_part < pcw) {
+          mx = start;
+          stop = true;
+          break;
+        } else {
+          position = start;
+          left_weight = pcw;
+          found = true;
+          break;
+        }
       }
     }
     if (!found && mn + 1 >= mx) {
@@ -184,6 +289,7 @@ __global__ void grid_median_kernel(GNode *level_nodes, GNode *next_nodes, unsign
       found = true;
     }
   }
+  if (lane != 0) return;
   const unsigned long long split_position = position + nd.offset[coord];
   nd.split = 1;
   nd.position = split_position;
@@ -203,24 +309,54 @@ __global__ void grid_median_kernel(GNode *level_nodes, GNode *next_nodes, unsign
   }
 }
 
-// position_of (mod.rs:63-87) and part_of (rcb.rs:21-42, first axis 1)
-__global__ void grid_emit_kernel(unsigned long long len, int D, unsigned long long gx, unsigned long long gy,
-                                 const GNode *__restrict__ nodes, int levels, unsigned long long *__restrict__ part) {
-  for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < len;
-       c += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long pos[3] = {c % gx, D == 2 ? c / gx : (c / gx) % gy, D == 2 ? 0 : c / gx / gy};
-    unsigned long long id = 0, i = 0;
-    int coord = 1;
-    for (int l = 0; l < levels; ++l) {
-      const GNode &nd = nodes[((1ull << l) - 1) + i];
-      if (!nd.split) break;
-      const unsigned long long right = pos[coord] < nd.position ? 0 : 1;
-      id = 2 * id + right;
-      i = 2 * i + right;
-      coord = (coord + 1) % D;
-    }
-    part[c] = id;
+// position_of (mod.rs:63-87) and part_of (rcb.rs:21-42, first axis 1).  A thread takes four consecutive cells of a row
+// (x from threadIdx, y and z from the block index: no division per cell) and walks the tree once for the first of
+// them, keeping the x-range of the box it ends in: the cells of the group inside that range share the id (parts are
+// boxes, a few hundred cells wide), the others walk again.
+constexpr int EMIT_CELLS = 4;
+__device__ __forceinline__ unsigned long long grid_part_of(const GNode *__restrict__ nodes, int levels, int D,
+                                                           const unsigned long long (&pos)[3], unsigned long long &x_end) {
+  unsigned long long id = 0, i = 0;
+  int coord = 1;
+  x_end = ~0ull;
+  for (int l = 0; l < levels; ++l) {
+    const GNode &nd = nodes[((1ull << l) - 1) + i];
+    if (!nd.split) break;
+    const unsigned long long p = nd.position;
+    const unsigned long long right = pos[coord] < p ? 0 : 1;
+    if (coord == 0 && !right) x_end = min(x_end, p);
+    id = 2 * id + right;
+    i = 2 * i + right;
+    coord = (coord + 1) % D;
   }
+  return id;
+}
+__global__ void grid_emit_kernel(int D, unsigned long long gx, unsigned long long gy, unsigned long long gz,
+                                 const GNode *__restrict__ nodes, int levels, unsigned long long *__restrict__ part) {
+  const unsigned long long x0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * EMIT_CELLS;
+  if (x0 >= gx) return;
+  for (unsigned long long z = blockIdx.z; z < gz; z += gridDim.z)
+    for (unsigned long long y = blockIdx.y; y < gy; y += gridDim.y) {
+      unsigned long long pos[3] = {x0, y, z}, x_end, id[EMIT_CELLS];
+      id[0] = grid_part_of(nodes, levels, D, pos, x_end);
+#pragma unroll
+      for (int j = 1; j < EMIT_CELLS; ++j) {
+        id[j] = id[j - 1];
+        if (x0 + j >= x_end && x0 + j < gx) {
+          pos[0] = x0 + j;
+          id[j] = grid_part_of(nodes, levels, D, pos, x_end);
+        }
+      }
+      unsigned long long *dst = part + x0 + gx * (y + gy * z);
+      if (x0 + EMIT_CELLS <= gx && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        reinterpret_cast<ulonglong2 *>(dst)[0] = make_ulonglong2(id[0], id[1]);
+        reinterpret_cast<ulonglong2 *>(dst)[1] = make_ulonglong2(id[2], id[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < EMIT_CELLS; ++j)
+          if (x0 + j < gx) dst[j] = id[j];
+      }
+    }
 }
 
 struct Buf {
@@ -251,7 +387,8 @@ void grid_levels(cudaStream_t st, GridScratch &S, int D, const unsigned long lon
   GNode *nodes = static_cast<GNode *>(S.nodes.p);
   S.err.ensure(16);
   GCU(cudaMemsetAsync(S.err.p, 0, 4, st));
-  grid_rowsum_kernel<W><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(w, g[0], rows, static_cast<W *>(S.rows.p));
+  grid_rowsum_kernel<W><<<(unsigned)std::min<unsigned long long>(148 * 16, (rows + TILE_ROWS * TILE_WARPS - 1) / (TILE_ROWS * TILE_WARPS)), 32 * TILE_WARPS, 0, st>>>(
+      w, g[0], rows, static_cast<W *>(S.rows.p));
   grid_root_kernel<W><<<1, 32, 0, st>>>(static_cast<const W *>(S.rows.p), rows, nodes, g[0], g[1], g[2]);
   for (size_t l = 0; l <= iters; ++l) {  // level `iters` only marks its boxes Whole
     const int coord = (int)((1 + l) % D), left = (int)(iters - l);
@@ -260,15 +397,18 @@ void grid_levels(cudaStream_t st, GridScratch &S, int D, const unsigned long lon
     GNode *cur = nodes + (((size_t)1 << l) - 1), *nxt = l < iters ? nodes + (((size_t)2 << l) - 1) : nullptr;
     if (left > 0) {
       S.axis.ensure((size_t)n_nodes * side * 8);
-      const unsigned by = (unsigned)std::min<unsigned long long>(65535, (side + 127) / 128);
+      // blocks along the axis: 128 positions each, 32 (four warps x eight rows) on the tiled path of axis 1
+      const unsigned by = (unsigned)std::min<unsigned long long>(65535, coord == 1 ? (side + 31) / 32 : (side + 127) / 128);
       grid_axis_kernel<W><<<dim3(n_nodes, by), 128, 0, st>>>(w, cur, D, coord, g[0], g[1], side, left, static_cast<W *>(S.axis.p));
     }
-    grid_median_kernel<W><<<(n_nodes + 63) / 64, 64, 0, st>>>(cur, nxt, n_nodes, coord, D, side, left, threads,
+    grid_median_kernel<W><<<(n_nodes + 3) / 4, 128, 0, st>>>(cur, nxt, n_nodes, coord, D, side, left, threads,
                                                               static_cast<const W *>(S.axis.p), static_cast<unsigned *>(S.err.p));
   }
   (void)max_side;
-  const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(148 * 16, (len + 255) / 256));
-  grid_emit_kernel<<<grid, 256, 0, st>>>(len, D, g[0], g[1], nodes, (int)iters, part);
+  (void)len;
+  const dim3 egrid((unsigned)((g[0] + 256 * EMIT_CELLS - 1) / (256 * EMIT_CELLS)), (unsigned)std::min<unsigned long long>(g[1], 65535),
+                   (unsigned)std::min<unsigned long long>(g[2], 65535));
+  grid_emit_kernel<<<egrid, 256, 0, st>>>(D, g[0], g[1], g[2], nodes, (int)iters, part);
 }
 
 int grid_rcb_run(int device, cudaStream_t st, uint64_t *part_dev, int D, const uint64_t *sizes, int wtype,

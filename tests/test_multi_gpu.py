@@ -47,14 +47,14 @@ def _worker(rank, world, port, cases, out):
                 algo.partition(again, (torch.from_numpy(pts[b:e].copy()).to(dev), tw))
                 assert torch.equal(again, part)
             st = ctx.stats()
-            results.append((part.cpu().numpy().astype(np.uint64), st["peer_exchange"], st["n_global"]))
+            results.append((part.cpu().numpy().astype(np.uint64), st["peer_exchange"], st["n_global"], list(st["matrix"])))
         out.put((rank, results))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def run_sharded(cases, world=2):
+def run_sharded(cases, world=2, want_matrix=False):
     """Runs every case (pts, w, iters, tol, rib, empty_last, peer) in ONE process group of `world` ranks (a
     rendezvous and an NCCL set-up cost ten seconds) and returns the concatenated ids of each."""
     import torch.multiprocessing as mp
@@ -75,7 +75,12 @@ def run_sharded(cases, world=2):
     for i, case in enumerate(cases):
         assert all(r[1][i][1] == int(case[6]) for r in res), "peer-memory exchange was requested but not used (or the reverse)"
         assert all(r[1][i][2] == case[0].shape[0] for r in res)
-        out.append(np.concatenate([r[1][i][0] for r in res]))
+        ids = np.concatenate([r[1][i][0] for r in res])
+        if want_matrix:
+            assert all(r[1][i][3] == res[0][1][i][3] for r in res), "the ranks applied different matrices"
+            out.append((ids, res[0][1][i][3]))
+        else:
+            out.append(ids)
     return out
 
 
@@ -140,7 +145,7 @@ def test_sharded_rcb_matches_oracle(oracle, world, peer):
             assert np.array_equal(got, oracle.rcb(pts, w, iters, tol, mode=0)), spec
 
 
-def test_sharded_rib_matches_single_gpu(two_gpus):
+def test_sharded_rib_matches_single_gpu(two_gpus, oracle):
     import coupe_b200
 
     rng = np.random.default_rng(12)
@@ -149,13 +154,25 @@ def test_sharded_rib_matches_single_gpu(two_gpus):
     c, s = np.cos(0.7), np.sin(0.7)
     pts = pts @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]]).T
     w = rng.integers(1, 10, n).astype(np.int64)
-    got = run_sharded([(pts, w, 6, 0.05, True, False, True)])[0]
+    got, mat = run_sharded([(pts, w, 6, 0.05, True, False, True)], want_matrix=True)[0]
+    mat = np.array(mat).reshape(3, 3)
+    # the oracle's matrix (moment sums in another order, another eigen solver: not pinned to the bit) agrees to rounding
+    want, omat = oracle.rib(pts, w, 6, 0.05, return_matrix=True)
+    np.testing.assert_allclose(mat, omat, atol=1e-9)
+    # given the matrix every rank applied, the sharded ids are those of the oracle's RCB on the mapped points: bit-exact
+    mapped = np.empty_like(pts)
+    for r in range(3):
+        acc = mat[r, 0] * pts[:, 0]
+        for k in range(1, 3):
+            acc = acc + mat[r, k] * pts[:, k]
+        mapped[:, r] = acc
+    assert np.array_equal(got, oracle.rcb(mapped, w, 6, 0.05))
+    # and they differ from the oracle's own RIB and from the single-GPU run only for points within rounding of a cut plane
+    assert (got != want).mean() < 1e-4
     dev = torch.device("cuda", 0)
     part = torch.empty(n, dtype=torch.int64, device=dev)
     coupe_b200.Rib(6, 0.05).partition(part, (torch.from_numpy(pts).to(dev), torch.from_numpy(w).to(dev)))
     one = part.cpu().numpy().astype(np.uint64)
-    # the moment sums are f64 and depend on the shard boundaries in the last bits: ids may differ
-    # only for points within rounding of a cut plane
     assert (got != one).mean() < 1e-4
 
 
