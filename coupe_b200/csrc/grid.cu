@@ -374,7 +374,8 @@ struct Buf {
 struct GridScratch {
   Buf nodes, axis, rows, w, part, err;
 };
-std::mutex g_grid_mu;
+std::mutex g_grid_mu;       // the scratch of a device while kernels use it
+std::mutex g_grid_host_mu;  // the host entry point's device copies (held for the whole call, outside g_grid_mu)
 GridScratch g_grid[64];
 
 template <class W>
@@ -468,6 +469,7 @@ int coupe_b200_grid_rcb_host(coupe_b200_ctx *ctx, uint64_t *part, uintptr_t dim,
   return grid_guard([&] {
     const int device = coupe_b200_ctx_device(ctx);
     GCU(cudaSetDevice(device));
+    std::lock_guard<std::mutex> host_lock(g_grid_host_mu);
     size_t len = sizes[0] * sizes[1] * (dim == 3 ? sizes[2] : 1);
     void *dw = nullptr, *dp = nullptr;
     {

@@ -389,11 +389,17 @@ __global__ void mj_emit_kernel(size_t n, const unsigned long long *__restrict__ 
     part[pay[j] & 0xFFFFFFFFull] = find_entry(start, entries, j);
 }
 
-__global__ void mj_axis_keys_kernel(size_t len, int D, int axis, const double *__restrict__ pts,
+__global__ void mj_axis_keys_kernel(size_t len, int D, int axis, const double *__restrict__ pts, size_t n_points,
                                     const unsigned long long *__restrict__ perm, unsigned long long *__restrict__ key,
-                                    unsigned long long *__restrict__ pay) {
+                                    unsigned long long *__restrict__ pay, uint32_t *err) {
   for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += (size_t)gridDim.x * blockDim.x) {
     const unsigned long long idx = perm[j];
+    if (idx >= n_points) {  // `points[*i1]` out of bounds: the reference panics
+      *err = 1;
+      key[j] = 0;
+      pay[j] = idx;
+      continue;
+    }
     key[j] = f64_key(pts[idx * D + axis]);
     pay[j] = idx;
   }
@@ -421,7 +427,8 @@ struct MjScratch {
   std::vector<cudaEvent_t> ev;  // [0], [1]: the whole call; then one pair per level around the sort passes
   double ms[3] = {0, 0, 0};
 };
-std::mutex g_mj_mu;
+std::mutex g_mj_mu;        // the scratch of a device while kernels use it
+std::mutex g_mj_host_mu;   // the host entry points' device copies (held for the whole call, outside g_mj_mu)
 MjScratch g_mj[64];
 
 int grid_for(size_t n, int threads) { return (int)std::max<size_t>(1, std::min<size_t>(148 * 16, (n + threads - 1) / threads)); }
@@ -633,6 +640,7 @@ int coupe_b200_multi_jagged_host(coupe_b200_ctx *ctx, uint64_t *part, uintptr_t 
   return mj_guard([&] {
     const int device = coupe_b200_ctx_device(ctx);
     MCU(cudaSetDevice(device));
+    std::lock_guard<std::mutex> host_lock(g_mj_host_mu);
     double *dp = nullptr, *dw = nullptr;
     uint64_t *dpart = nullptr;
     {
@@ -659,7 +667,6 @@ int coupe_b200_axis_sort_device(coupe_b200_ctx *ctx, void *stream, uintptr_t dim
   if (!ctx) return COUPE_ERR_CRASH;
   if (dim != 2 && dim != 3) return COUPE_ERR_BAD_DIMENSION;
   if (coord >= dim) return COUPE_ERR_CRASH;  // the reference indexes out of the point: panic
-  (void)n_points;
   if (len == 0) return COUPE_ERR_OK;
   if (!points_dev || !permutation_dev) return COUPE_ERR_CRASH;
   return mj_guard([&] {
@@ -676,8 +683,14 @@ int coupe_b200_axis_sort_device(coupe_b200_ctx *ctx, void *stream, uintptr_t dim
     S.hist.ensure(((size_t)RADIX * tiles + 2 * RADIX) * 4);
     unsigned long long *ka = S.key_a.as<unsigned long long>(), *kb = S.key_b.as<unsigned long long>();
     unsigned long long *pa = S.pay_a.as<unsigned long long>(), *pb = S.pay_b.as<unsigned long long>();
-    mj_axis_keys_kernel<<<grid_for(len, 256), 256, 0, st>>>(len, (int)dim, (int)coord, points_dev,
-                                                             reinterpret_cast<const unsigned long long *>(permutation_dev), ka, pa);
+    S.small.ensure(16);
+    uint32_t *err = S.small.as<uint32_t>(), herr = 0;
+    MCU(cudaMemsetAsync(err, 0, 4, st));
+    mj_axis_keys_kernel<<<grid_for(len, 256), 256, 0, st>>>(len, (int)dim, (int)coord, points_dev, n_points,
+                                                             reinterpret_cast<const unsigned long long *>(permutation_dev), ka, pa, err);
+    MCU(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st));
+    MCU(cudaStreamSynchronize(st));
+    if (herr) return (int)COUPE_ERR_CRASH;  // the permutation is left as it was
     radix_sort(st, len, ka, pa, kb, pb, S.hist.as<uint32_t>(), {0, 1, 2, 3, 4, 5, 6, 7});
     MCU(cudaMemcpyAsync(permutation_dev, pa, len * 8, cudaMemcpyDeviceToDevice, st));
     MCU(cudaStreamSynchronize(st));

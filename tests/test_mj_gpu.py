@@ -64,6 +64,19 @@ def test_axis_sort_is_stable_and_matches_the_oracle(cb, oracle):
         assert np.array_equal(perm.cpu().numpy().astype(np.uint64), oracle.mj_axis_sort(pts, start, coord))
 
 
+def test_axis_sort_rejects_an_index_outside_the_points(cb):
+    dev = torch.device("cuda", 0)
+    pts = torch.rand((100, 2), dtype=torch.float64, device=dev)
+    perm = torch.arange(100, dtype=torch.int64, device=dev)
+    perm[17] = 100  # `points[*i1]` out of bounds: the reference panics
+    before = perm.clone()
+    with pytest.raises(cb.BackendError):
+        cb.axis_sort(pts, perm, 0)
+    assert torch.equal(perm, before)
+    with pytest.raises(cb.BackendError):
+        cb.axis_sort(pts, torch.arange(100, dtype=torch.int64, device=dev), 2)  # no such coordinate
+
+
 CASES = [
     # n, dim, part_count, max_iter, points, weights
     (1, 2, 1, 1, "uniform", "int"),
