@@ -171,18 +171,28 @@ __global__ void __launch_bounds__(RADIX) radix_scan_digits_kernel(const uint32_t
 
 // Stable scatter of one tile.  Warp w owns the w-th run of 32 * SORT_ITEMS consecutive elements of the tile
 // and keeps them in registers: (1) every warp counts the digits of its run, (2) one scan per digit over the
-// warps in order, from the tile's global offset of that digit, gives every warp its first place per digit,
-// (3) every warp places its elements round by round, in order.  Two block barriers per tile; an element's
-// place is (tile offset of its digit) + (elements of that digit in front of it in the tile).
+// warps in order gives every warp its first LOCAL place per digit (the tile sorted by digit), (3) every warp
+// puts its elements there, round by round, in shared memory, (4) the tile is written out linearly: consecutive
+// threads hold consecutive elements of the sorted tile, i.e. runs of one digit, whose global places are
+// consecutive too -> coalesced stores (each thread storing its own element where it belongs cost 255 us per
+// pass at 10^7 elements: 32 different streams per warp).  An element's global place is
+// (global offset of its digit for this tile) + (its place among the tile's elements of that digit).
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+static_assert(RADIX == SORT_THREADS, "one thread per digit in the scans of the scatter");
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(size_t n, const unsigned long long *__restrict__ key_in, const unsigned long long *__restrict__ pay_in,
                      unsigned long long *__restrict__ key_out, unsigned long long *__restrict__ pay_out, int pass,
                      const uint32_t *__restrict__ offs, const uint32_t *__restrict__ base) {
-  __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];  // per warp: elements of the digit in its run, then its next free place
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem_raw);                 // [SORT_TILE]
+  unsigned long long *s_pay = s_key + SORT_TILE;                                                // [SORT_TILE]
+  uint32_t(*s_cnt)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(s_pay + SORT_TILE);           // [SORT_WARPS][RADIX]
+  uint32_t *s_goff = reinterpret_cast<uint32_t *>(s_cnt + SORT_WARPS);                          // [RADIX] global - local
+  uint32_t *s_scan = s_goff + RADIX;                                                            // [RADIX]
   for (int w = 0; w < SORT_WARPS; ++w) s_cnt[w][threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t tile = (size_t)SORT_THREADS * SORT_ITEMS, lo = blockIdx.x * tile, hi = min(n, lo + tile);
+  const size_t lo = (size_t)blockIdx.x * SORT_TILE, hi = min(n, lo + (size_t)SORT_TILE);
   const size_t run0 = lo + (size_t)warp * 32 * SORT_ITEMS;
   unsigned long long k[SORT_ITEMS], p[SORT_ITEMS];
 #pragma unroll
@@ -204,13 +214,26 @@ radix_scatter_kernel(size_t n, const unsigned long long *__restrict__ key_in, co
     __syncwarp();
   }
   __syncthreads();
-  {  // thread = digit: the warps' first places, in warp order
-    uint32_t run = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x] + base[threadIdx.x];
+  {  // thread = digit: elements of the digit in the tile, and every warp's place among them
+    uint32_t run = 0;
     for (int w = 0; w < SORT_WARPS; ++w) {
       const uint32_t c = s_cnt[w][threadIdx.x];
       s_cnt[w][threadIdx.x] = run;
       run += c;
     }
+    s_scan[threadIdx.x] = run;
+  }
+  __syncthreads();
+  for (int d = 1; d < RADIX; d <<= 1) {  // inclusive scan of the digit counts (RADIX == SORT_THREADS)
+    const uint32_t v = threadIdx.x >= (unsigned)d ? s_scan[threadIdx.x - d] : 0u;
+    __syncthreads();
+    s_scan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  {
+    const uint32_t local_start = threadIdx.x ? s_scan[threadIdx.x - 1] : 0u;
+    for (int w = 0; w < SORT_WARPS; ++w) s_cnt[w][threadIdx.x] += local_start;  // local places in the sorted tile
+    s_goff[threadIdx.x] = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x] + base[threadIdx.x] - local_start;
   }
   __syncthreads();
 #pragma unroll
@@ -222,12 +245,20 @@ radix_scatter_kernel(size_t n, const unsigned long long *__restrict__ key_in, co
       const uint32_t d = digit_of(k[r], p[r], pass);
       const uint32_t peers = __match_any_sync(vmask, d);
       const uint32_t dst = s_cnt[warp][d] + __popc(peers & ((1u << lane) - 1));
-      key_out[dst] = k[r];
-      pay_out[dst] = p[r];
+      s_key[dst] = k[r];
+      s_pay[dst] = p[r];
       __syncwarp(vmask);  // every peer has read the place before its first lane moves it on
       if ((int)lane == __ffs(peers) - 1) s_cnt[warp][d] += __popc(peers);
     }
     __syncwarp();
+  }
+  __syncthreads();
+  const uint32_t count = (uint32_t)(hi - lo);
+  for (uint32_t i = threadIdx.x; i < count; i += SORT_THREADS) {
+    const unsigned long long kk = s_key[i], pp = s_pay[i];
+    const uint32_t g = s_goff[digit_of(kk, pp, pass)] + i;
+    key_out[g] = kk;
+    pay_out[g] = pp;
   }
 }
 
@@ -439,12 +470,21 @@ void radix_sort(cudaStream_t st, size_t n, unsigned long long *&ka, unsigned lon
   const size_t tile = (size_t)SORT_THREADS * SORT_ITEMS;
   const unsigned tiles = (unsigned)((n + tile - 1) / tile);
   if (!tiles) return;
+  // the scatter stages its tile in shared memory: 2 x 32 KB of elements + the per-warp digit counters
+  constexpr int SCATTER_SMEM = SORT_TILE * 16 + (SORT_WARPS + 2) * RADIX * (int)sizeof(uint32_t);
+  static bool attr_set[64] = {false};  // (a function attribute is per device)
+  int dev = 0;
+  MCU(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    MCU(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCATTER_SMEM));
+    attr_set[dev & 63] = true;
+  }
   for (int pass : passes) {
     uint32_t *totals = hist + (size_t)RADIX * tiles, *base = totals + RADIX;
     radix_hist_kernel<<<tiles, SORT_THREADS, 0, st>>>(n, ka, pa, pass, hist);
     radix_scan_rows_kernel<<<RADIX, SORT_THREADS, 0, st>>>(hist, tiles, totals);
     radix_scan_digits_kernel<<<1, RADIX, 0, st>>>(totals, base);
-    radix_scatter_kernel<<<tiles, SORT_THREADS, 0, st>>>(n, ka, pa, kb, pb, pass, hist, base);
+    radix_scatter_kernel<<<tiles, SORT_THREADS, SCATTER_SMEM, st>>>(n, ka, pa, kb, pb, pass, hist, base);
     std::swap(ka, kb);
     std::swap(pa, pb);
   }
