@@ -314,40 +314,49 @@ grid_median_kernel(GNode *level_nodes, GNode *next_nodes, unsigned nodes, int co
 // them, keeping the x-range of the box it ends in: the cells of the group inside that range share the id (parts are
 // boxes, a few hundred cells wide), the others walk again.
 constexpr int EMIT_CELLS = 4;
-__device__ __forceinline__ unsigned long long grid_part_of(const GNode *__restrict__ nodes, int levels, int D,
-                                                           const unsigned long long (&pos)[3], unsigned long long &x_end) {
-  unsigned long long id = 0, i = 0;
+constexpr uint32_t CUT_WHOLE = 0xFFFFFFFFu;
+// the tree as one 32-bit word per node for the emit pass: the split position, CUT_WHOLE for a box that is not split
+// (grid sides are below 2^32 - 1: checked on the host)
+__global__ void grid_cuts_kernel(const GNode *__restrict__ nodes, unsigned long long count, uint32_t *__restrict__ cuts) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) cuts[i] = nodes[i].split ? (uint32_t)nodes[i].position : CUT_WHOLE;
+}
+__device__ __forceinline__ uint32_t grid_part_of(const uint32_t *__restrict__ cuts, int levels, int D, const uint32_t (&pos)[3],
+                                                 uint32_t &x_end) {
+  uint32_t id = 0, i = 0, first = 0;  // first: index of the level's first node, 2^l - 1
   int coord = 1;
-  x_end = ~0ull;
+  x_end = 0xFFFFFFFFu;
   for (int l = 0; l < levels; ++l) {
-    const GNode &nd = nodes[((1ull << l) - 1) + i];
-    if (!nd.split) break;
-    const unsigned long long p = nd.position;
-    const unsigned long long right = pos[coord] < p ? 0 : 1;
+    const uint32_t p = __ldg(cuts + first + i);
+    if (p == CUT_WHOLE) break;
+    const uint32_t right = pos[coord] < p ? 0u : 1u;
     if (coord == 0 && !right) x_end = min(x_end, p);
     id = 2 * id + right;
     i = 2 * i + right;
-    coord = (coord + 1) % D;
+    first = 2 * first + 1;
+    coord = coord + 1 == D ? 0 : coord + 1;
   }
   return id;
 }
-__global__ void grid_emit_kernel(int D, unsigned long long gx, unsigned long long gy, unsigned long long gz,
-                                 const GNode *__restrict__ nodes, int levels, unsigned long long *__restrict__ part) {
-  const unsigned long long x0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * EMIT_CELLS;
-  if (x0 >= gx) return;
-  for (unsigned long long z = blockIdx.z; z < gz; z += gridDim.z)
-    for (unsigned long long y = blockIdx.y; y < gy; y += gridDim.y) {
-      unsigned long long pos[3] = {x0, y, z}, x_end, id[EMIT_CELLS];
-      id[0] = grid_part_of(nodes, levels, D, pos, x_end);
+__global__ void grid_emit_kernel(int D, uint32_t gx, uint32_t gy, uint32_t gz, const uint32_t *__restrict__ cuts, int levels,
+                                 unsigned long long *__restrict__ part) {
+  const unsigned long long x0l = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * EMIT_CELLS;
+  if (x0l >= gx) return;
+  const uint32_t x0 = (uint32_t)x0l;
+  for (uint32_t z = blockIdx.z; z < gz; z += gridDim.z)
+    for (uint32_t y = blockIdx.y; y < gy; y += gridDim.y) {
+      uint32_t pos[3] = {x0, y, z}, x_end;
+      unsigned long long id[EMIT_CELLS];
+      id[0] = grid_part_of(cuts, levels, D, pos, x_end);
 #pragma unroll
       for (int j = 1; j < EMIT_CELLS; ++j) {
         id[j] = id[j - 1];
         if (x0 + j >= x_end && x0 + j < gx) {
           pos[0] = x0 + j;
-          id[j] = grid_part_of(nodes, levels, D, pos, x_end);
+          id[j] = grid_part_of(cuts, levels, D, pos, x_end);
         }
       }
-      unsigned long long *dst = part + x0 + gx * (y + gy * z);
+      unsigned long long *dst = part + x0 + (unsigned long long)gx * (y + (unsigned long long)gy * z);
       if (x0 + EMIT_CELLS <= gx && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         reinterpret_cast<ulonglong2 *>(dst)[0] = make_ulonglong2(id[0], id[1]);
         reinterpret_cast<ulonglong2 *>(dst)[1] = make_ulonglong2(id[2], id[3]);
@@ -372,7 +381,7 @@ struct Buf {
   }
 };
 struct GridScratch {
-  Buf nodes, axis, rows, w, part, err;
+  Buf nodes, axis, rows, w, part, err, cuts;
 };
 std::mutex g_grid_mu;       // the scratch of a device while kernels use it
 std::mutex g_grid_host_mu;  // the host entry point's device copies (held for the whole call, outside g_grid_mu)
@@ -409,7 +418,11 @@ void grid_levels(cudaStream_t st, GridScratch &S, int D, const unsigned long lon
   (void)len;
   const dim3 egrid((unsigned)((g[0] + 256 * EMIT_CELLS - 1) / (256 * EMIT_CELLS)), (unsigned)std::min<unsigned long long>(g[1], 65535),
                    (unsigned)std::min<unsigned long long>(g[2], 65535));
-  grid_emit_kernel<<<egrid, 256, 0, st>>>(D, g[0], g[1], g[2], nodes, (int)iters, part);
+  const unsigned long long n_tree = ((unsigned long long)2 << iters) - 1;  // levels 0 .. iters
+  S.cuts.ensure(n_tree * sizeof(uint32_t));
+  grid_cuts_kernel<<<(unsigned)((n_tree + 255) / 256), 256, 0, st>>>(nodes, n_tree, static_cast<uint32_t *>(S.cuts.p));
+  grid_emit_kernel<<<egrid, 256, 0, st>>>(D, (uint32_t)g[0], (uint32_t)g[1], (uint32_t)g[2], static_cast<const uint32_t *>(S.cuts.p),
+                                          (int)iters, part);
 }
 
 int grid_rcb_run(int device, cudaStream_t st, uint64_t *part_dev, int D, const uint64_t *sizes, int wtype,
@@ -420,6 +433,7 @@ int grid_rcb_run(int device, cudaStream_t st, uint64_t *part_dev, int D, const u
   if (iters > 24) return COUPE_ERR_ALLOC;   // node tables of 2^iter_count entries
   const unsigned long long g[3] = {sizes[0], sizes[1], D == 3 ? sizes[2] : 1ull};
   if (!g[0] || !g[1] || !g[2]) return COUPE_ERR_CRASH;  // NonZeroUsize
+  if (g[0] >= 0xFFFFFFFFull || g[1] >= 0xFFFFFFFFull || g[2] >= 0xFFFFFFFFull) return COUPE_ERR_ALLOC;  // 32-bit cut positions in the emit pass
   GCU(cudaSetDevice(device));
   std::lock_guard<std::mutex> lock(g_grid_mu);
   GridScratch &S = g_grid[device];
