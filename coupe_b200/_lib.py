@@ -170,7 +170,10 @@ def lib():
     L.coupe_b200_free.argtypes = [C.c_void_p]
     L.coupe_b200_parse_rcb_spec.restype = C.c_int
     L.coupe_b200_parse_rcb_spec.argtypes = [C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
-    # include/coupe_b200_mj.h
+    # include/coupe_b200_mj.h (absent from older builds loaded through COUPE_B200_LIB for A/B timing)
+    if not hasattr(L, "coupe_b200_multi_jagged_device"):
+        _lib = L
+        return L
     L.coupe_b200_multi_jagged_device.restype = C.c_int
     L.coupe_b200_multi_jagged_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                                  C.c_void_p, C.c_size_t, C.c_size_t]
