@@ -244,7 +244,9 @@ struct coupe_b200_ctx {
   int table_rep_max = 3; // experiments: cap on the bank-private copies of the per-parent table (log2)
   int carve_fit = 1;     // keep the dense sweeps under the 196 KB shared-memory carve-out when the tables allow it
   int sample_w_opt = 1;  // f64 weights: max |w| from a sample, verified by the root sweep
-  int defer_opt = 1;     // undecided levels: the next dense sweep lists the points of the undecided bins (no rescan of idx)
+  int defer_opt = 1;     // undecided levels: the next dense sweep lists the points of the undecided bins (no rescan of idx);
+                         // 2: the deferring variant of the sweep at every level (no prediction)
+  std::vector<uint8_t> undecided_last;  // per level: the context's previous call left it undecided after its dense pass
   std::vector<cudaEvent_t> events;  // time_sweeps: start/stop pairs
   std::vector<int> event_kind;      // 0 dense, 1 refine
   std::vector<int> event_level;     // tree level of the sweep
@@ -278,6 +280,12 @@ constexpr size_t SMEM_CARVE_196 = 196 * 1024 - 1024;
 template <int WIN, bool ROOT>
 void launch_sweep(bool smem, bool tsm, bool idx16, int grid, size_t bytes, cudaStream_t st,
                   const SweepArgs &a) {
+  constexpr bool DEFERRABLE = !ROOT && (WIN == WIN_I32 || WIN == WIN_CONST);
+  if (DEFERRABLE && smem && a.def_rec) {  // the variant that lists the points of undecided bins
+    if (idx16) launch_pdl(sweep_kernel<WIN, true, ROOT, true, uint16_t, DEFERRABLE>, grid, SWEEP_THREADS, bytes, st, a);
+    else launch_pdl(sweep_kernel<WIN, true, ROOT, true, uint32_t, DEFERRABLE>, grid, SWEEP_THREADS, bytes, st, a);
+    return;
+  }
   if (smem && idx16) launch_pdl(sweep_kernel<WIN, true, ROOT, true, uint16_t>, grid, SWEEP_THREADS, bytes, st, a);
   else if (smem) launch_pdl(sweep_kernel<WIN, true, ROOT, true, uint32_t>, grid, SWEEP_THREADS, bytes, st, a);
   else if (tsm) launch_pdl(sweep_kernel<WIN, false, ROOT, true, uint32_t>, grid, SWEEP_THREADS, bytes, st, a);
@@ -319,6 +327,10 @@ void prepare_funcs(coupe_b200_ctx *c) {
   SETATTR((sweep_kernel<win, true, root, true, uint32_t>));         \
   SETATTR((sweep_kernel<win, false, root, true, uint32_t>));        \
   SETATTR((sweep_kernel<win, false, root, false, uint32_t>))
+  SETATTR((sweep_kernel<WIN_I32, true, false, true, uint16_t, true>));
+  SETATTR((sweep_kernel<WIN_I32, true, false, true, uint32_t, true>));
+  SETATTR((sweep_kernel<WIN_CONST, true, false, true, uint16_t, true>));
+  SETATTR((sweep_kernel<WIN_CONST, true, false, true, uint32_t, true>));
   SETALL(WIN_I32, true);
   SETALL(WIN_I64, true);
   SETALL(WIN_F64, true);
@@ -844,8 +856,22 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     return enqueue_reduce_walk(level, guard);
   };
   // --- deferred points: the level below an undecided one has listed the points of the undecided bins ---
-  auto can_defer = [&](int level_next) {
+  // The deferring variant of the sweep costs the levels that have nothing to defer ~6 % (rcb_kernels.cuh: DEFER), so
+  // it is launched only below a level that is EXPECTED to stay undecided: one that resolves fewer candidates per
+  // pass than the first levels do, or one that the previous call on this context left undecided (the calls of a
+  // context are collective, so every rank predicts alike).  A level that stays undecided against the prediction is
+  // refined by rescanning; the results do not depend on the choice.
+  std::vector<uint8_t> undecided_now((size_t)L, 0);
+  auto defer_possible = [&](int level_next) {
     return defer_call && level_next < L && plan_first(c, level_next).smem && (win == WIN_I32 || win == WIN_CONST);
+  };
+  auto can_defer = [&](int level_next) {  // ... and predicted to pay
+    if (!defer_possible(level_next)) return false;
+    if (c->defer_opt >= 2) return true;
+    const int lv = level_next - 1;
+    const bool few_bits = plan_first(c, lv).k < plan_first(c, 0).k;
+    const bool last_time = (int)c->undecided_last.size() == L && c->undecided_last[(size_t)lv] != 0;
+    return few_bits || last_time;
   };
   auto defer_args = [&](int level_next) {
     DeferArgs d{};
@@ -996,6 +1022,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
       speculated = true;
     }
     uint32_t unresolved = wait_flag(pending);
+    undecided_now[(size_t)level] = unresolved > 0 ? 1 : 0;
     for (int redo = 0; level == 0 && rescale; ++redo) {
       // the sample of the weights gave another fixed-point form or scale than all of them do (an
       // outlier, a negative or a tiny weight outside the sample), or the wide form wants a finer root
@@ -1030,7 +1057,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
         wp = w32;
       }
     }
-    if (unresolved > 0 && (speculated ? spec_deferred : can_defer(level + 1))) {
+    if (unresolved > 0 && (speculated ? spec_deferred : defer_possible(level + 1))) {  // (not speculated: known undecided)
       // Deferred refinement: the dense sweep of level + 1 lists the points of the undecided bins; the
       // refinement passes of this level read that list, then the listed points take their child.
       if (!speculated) enqueue_dense(level + 1, k, nullptr, true);
@@ -1066,6 +1093,7 @@ int run_impl(coupe_b200_ctx *c, bool rib, cudaStream_t st, uint64_t *part_dev, u
     }
     pending = next_pending;
   }
+  c->undecided_last = undecided_now;
   CU(cudaMemcpyAsync(c->h_pinned + 2, &gp->refine_points, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned, &gp->shift, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_pinned + 6, &gp->ec, 4, cudaMemcpyDeviceToHost, st));
@@ -1531,7 +1559,7 @@ int coupe_b200_set_option(coupe_b200_ctx *c, const char *name, int64_t value) {
   else if (s == "peer_exchange") c->use_xchg_opt = value != 0;
   else if (s == "sample_weights") c->sample_w_opt = value != 0;
   else if (s == "carve_fit") c->carve_fit = value != 0;
-  else if (s == "defer") c->defer_opt = value != 0;
+  else if (s == "defer") c->defer_opt = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
   else if (s == "smem_pad") c->smem_pad = (int)std::max<int64_t>(0, std::min<int64_t>(32768, value));
   else if (s == "table_rep_max") c->table_rep_max = (int)std::max<int64_t>(0, std::min<int64_t>(3, value));
   else return COUPE_ERR_NOT_FOUND;

@@ -753,7 +753,10 @@ __device__ __forceinline__ size_t defer_append(uint32_t *s_cnt, uint32_t seg, ui
 }
 
 // TSM: the per-parent table is staged in shared memory (always in SMEM mode).
-template <int WIN, bool SMEM, bool ROOT, bool TSM, class IDX>
+// DEFER: the variant that can list the points of undecided bins ("Deferred points").  Its (cold) hit path raises the
+// register pressure of the hot loop: 233 instead of 216 instructions per group in rematerialised addresses and
+// constants, so it is only launched where a level is expected to stay undecided (engine.cu: can_defer).
+template <int WIN, bool SMEM, bool ROOT, bool TSM, class IDX, bool DEFER = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = a.k, level = a.level, kprev = a.kprev;
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(const __grid_co
   // Deferred points: a point of the ONE bin an undecided bisection of the level above narrowed down to does
   // not know its child yet (its parent's split position is NaN in the table).  It is appended to the block's
   // list with what the refinement of the parent and the later fix-up need, and contributes nothing here.
-  constexpr bool CAN_DEFER = !ROOT && SMEM && (WIN == WIN_I32 || WIN == WIN_CONST);
+  constexpr bool CAN_DEFER = DEFER && !ROOT && SMEM && (WIN == WIN_I32 || WIN == WIN_CONST);
   const bool defer_on = CAN_DEFER && a.def_rec != nullptr;
   uint32_t *s_defcnt = reinterpret_cast<uint32_t *>(smem_raw + (CAN_DEFER ? a.def_smem_off : 0));
   if (SMEM) {

@@ -24,7 +24,7 @@ def cb():
 @pytest.fixture(scope="module")
 def ctxs(cb):
     made = []
-    for opts in ({}, {"kmax_a": 2, "kmax_refine": 2}, {"kmax_a": 1, "kmax_refine": 1}, {"kmax_a": 2, "kmax_refine": 2, "defer": 0}):
+    for opts in ({}, {"kmax_a": 2, "kmax_refine": 2, "defer": 2}, {"kmax_a": 1, "kmax_refine": 1}, {"kmax_a": 2, "kmax_refine": 2, "defer": 0}):
         c = cb.Context(0)
         for k, v in opts.items():
             c.set_option(k, v)

@@ -510,23 +510,27 @@ def test_deferred_refinement(cb, oracle, wk, opts):
         want, tr = oracle.rcb(pts, w, iters, tol, mode=1, trace=True)
         v = tr.visited.astype(bool)
         seen = {}
-        for defer in (1, 0):
+        for defer in (2, 1, 0):  # 2: the deferring sweep at every level; 1: where a level is predicted to stay undecided; 0: never
             ctx = cb.Context(0)
             ctx.set_option("defer", defer)
             for k, val in opts.items():
                 ctx.set_option(k, val)
-            got = run_device(cb, pts, w, iters, tol, ctx=ctx)
-            assert np.array_equal(got, want), f"defer={defer}: {int((got != want).sum())} of {n} ids differ"
-            t = ctx.trace(iters)
-            assert np.array_equal(t["visited"], tr.visited)
-            assert np.array_equal(t["split_pos"][v], tr.split_pos[v])
-            assert np.array_equal(t["iters"][v], tr.iters[v])
-            assert np.array_equal(t["weight_left"][v], tr.weight_left[v])
-            seen[defer] = ctx.stats()
+            for call in range(2 if defer == 1 else 1):  # the second call predicts from the first one's undecided levels
+                got = run_device(cb, pts, w, iters, tol, ctx=ctx)
+                assert np.array_equal(got, want), f"defer={defer}: {int((got != want).sum())} of {n} ids differ"
+                t = ctx.trace(iters)
+                assert np.array_equal(t["visited"], tr.visited)
+                assert np.array_equal(t["split_pos"][v], tr.split_pos[v])
+                assert np.array_equal(t["iters"][v], tr.iters[v])
+                assert np.array_equal(t["weight_left"][v], tr.weight_left[v])
+                seen[(defer, call)] = ctx.stats()
             ctx.close()
-        assert seen[0]["deferred_levels"] == 0 and seen[0]["list_refine_sweeps"] == 0
-        if seen[0]["refine_sweeps"] > 1 or opts:  # (a refinement of the last level alone still scans)
-            assert seen[1]["deferred_levels"] > 0 and seen[1]["list_refine_sweeps"] > 0
+        assert seen[(0, 0)]["deferred_levels"] == 0 and seen[(0, 0)]["list_refine_sweeps"] == 0
+        assert seen[(1, 1)]["deferred_levels"] >= seen[(1, 0)]["deferred_levels"]
+        if seen[(0, 0)]["refine_sweeps"] > 1 or opts:  # (a refinement of the last level alone still scans)
+            assert seen[(2, 0)]["deferred_levels"] > 0 and seen[(2, 0)]["list_refine_sweeps"] > 0
+            # every level but the last that the first call left undecided is deferred by the second
+            assert seen[(1, 1)]["deferred_levels"] == seen[(2, 0)]["deferred_levels"]
 
 
 @pytest.mark.parametrize("dim", [2, 3])

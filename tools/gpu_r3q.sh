@@ -1,7 +1,7 @@
 #!/bin/bash
 # Instruction counts and times of the ten dense sweeps of one call; the deferred-point tests; live timing.
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -x -q -m gpu -k "deferred or fuzz or schedules or const" > gpurun_out/pytest_defer.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_defer.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -x -q -m gpu > gpurun_out/pytest_defer.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_defer.log
 tail -3 gpurun_out/pytest_defer.log
 timeout 600 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum --clock-control none -k regex:sweep_kernel -c 10 --csv --log-file gpurun_out/sweep_inst.csv python tools/quick_bench.py --n 125000000 --w f64 --dist gauss --reps 0 > /dev/null 2>&1
 python - <<'PY'
