@@ -1,5 +1,6 @@
-"""Regenerates the results table of BASELINE.md §4 from the bench lines kept under profiles/: r02b_bench_*.json (second
-half of round 2: deferred refinement) where one exists, else r02_bench_*.json."""
+"""Regenerates the results table of BASELINE.md §4 from the bench lines kept under profiles/: r02c_bench_*.json (the final code of round 2: the deferring
+sweep only where a level is predicted to stay undecided) where one exists, else r02b_bench_*.json (second half of round 2: deferred
+refinement), else r02_bench_*.json."""
 import json
 import os
 import re
@@ -8,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def load(name):
-    for tag in ("r02b", "r02"):
+    for tag in ("r02c", "r02b", "r02"):
         p = os.path.join(ROOT, "profiles", f"{tag}_bench_{name}.json")
         if os.path.exists(p):
             d = json.loads(open(p).read().strip().splitlines()[-1])
