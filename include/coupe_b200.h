@@ -164,7 +164,12 @@ int coupe_b200_reserve(coupe_b200_ctx *ctx, uintptr_t n, uintptr_t dim, uintptr_
  *   trace (1)                keep the split tree for coupe_b200_last_trace
  *   time_sweeps (0)          1: CUDA events around the dense sweeps, 2: refinement sweeps too, 3: and print them
  *   peer_exchange (1)        multi-GPU: histograms over peer memory (0: NCCL all-reduces)
- *   sample_weights (1)       f64 weights: fixed-point form and scale from a sample, verified by the root sweep */
+ *   sample_weights (1)       f64 weights: fixed-point form and scale from a sample, verified by the root sweep
+ *   defer (0..2, 1)          levels left undecided by their dense pass: 0 refine by rescanning the idx words; 1 the next
+ *                            level's dense sweep lists the points of the undecided bins (no rescan) where the level is
+ *                            predicted to stay undecided — fewer bits per pass than the first levels, or undecided in the
+ *                            context's previous call; 2 at every level.  The results do not depend on it.
+ *   carve_fit (1), smem_pad (0), table_rep_max (3)   experiments on the shared-memory layout of the dense sweeps */
 int coupe_b200_set_option(coupe_b200_ctx *ctx, const char *name, int64_t value);
 
 /* Library / build identification string. */
